@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ko():
+    """The CPU oracle (test infrastructure only)."""
+    from oracle import oracle as _ko
+
+    _ko.build()
+    _ko.set_threads(1)  # sequential-order sums => deterministic
+    return _ko
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "kat_numpy.json")) as f:
+        return json.load(f)
