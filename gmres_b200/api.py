@@ -1,0 +1,410 @@
+"""ctypes binding of include/krylov_b200.h and the Python mirror of the reference API.
+
+Every solver method keeps the reference procedure's name and argument order
+(citations are to the reference tree):
+
+    gmres_mgsr_omp(Ax_vec,b,x,m,tol,final_err,v_err,n_out,restart_out,M_inv,params)  src/gmres_mgsr.f90:277
+    gmres_mgsr_mf (...)                                                              src/gmres_mgsr.f90:98
+    gmres_hh_omp(Ax_vec,b,x,m,tol,final_err,v_err,n_out,stages_out)                  src/gmres_hh.f90:211
+    gmres_hh_prec_omp(...,m_inv,params)                                              src/gmres_hh.f90:388
+    cg / cg_omp (Ax_op,b,x,tol,iter,res)                                             src/cg.f90:11 / :83
+    pcg / pcg_omp (...,M_inv,params)                                                 src/cg.f90:44 / :154
+    bicgstab / pbicgstab / pbicgstab_omp                                             src/bicgstab.f90:12 / :49 / :91
+
+intent(out) arguments become fields of the returned result object.  Vectors may be
+numpy float64 arrays (host pointer mode; copied to and from the device inside the
+call) or CUDA torch.float64 tensors (device pointer mode; they stay in HBM).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libkrylov_b200.so"
+
+KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN = 0, 1, 2
+KL_OP_POISSON5, KL_OP_POISSON5_BRANCHY, KL_OP_ANISO5, KL_OP_USER = 0, 1, 2, 100
+KL_PC_NONE, KL_PC_CBPR2, KL_PC_CHEB, KL_PC_USER = 0, 1, 2, 100
+KL_POINTER_HOST, KL_POINTER_DEVICE = 0, 1
+(KL_OPT_ORTHO, KL_OPT_MAX_RESTARTS, KL_OPT_VERR, KL_OPT_CHECK_EVERY, KL_OPT_USE_GRAPH,
+ KL_OPT_HH_MODE, KL_OPT_FUSE) = range(1, 8)
+ORTHO_MGS2, ORTHO_CGS2, ORTHO_CGS2_SELECTIVE = 0, 1, 2
+HH_SEQUENTIAL, HH_BLOCKED = 0, 1
+KL_UNIQUE_ID_BYTES = 128
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+PRECOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                         C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_void_p)
+
+
+class kl_operator_t(C.Structure):
+    _fields_ = [("kind", C.c_int), ("eps_x", C.c_double), ("eps_y", C.c_double),
+                ("fn", APPLY_FN), ("user", C.c_void_p)]
+
+
+class kl_precond_t(C.Structure):
+    _fields_ = [("kind", C.c_int), ("degree", C.c_int), ("fn", PRECOND_FN), ("user", C.c_void_p)]
+
+
+class kl_stats_t(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("cycles", C.c_int), ("solve_ms", C.c_double),
+                ("total_ms", C.c_double), ("algorithmic_bytes", C.c_double),
+                ("kernel_launches", C.c_longlong), ("orth_frobenius", C.c_double),
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
+
+
+class KrylovError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.environ.get("KRYLOV_B200_LIB", os.path.join(_HERE, _LIBNAME))
+
+
+_lib = None
+
+
+def load_library():
+    """Load libkrylov_b200.so.  Raises (never falls back to a CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise KrylovError(
+            f"{path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; "
+            "g.build()' or make -C gmres_b200/csrc).  There is no CPU fallback.")
+    L = C.CDLL(path)
+    L.kl_last_error.restype = C.c_char_p
+    L.kl_last_error.argtypes = [C.c_void_p]
+    for name in ("kl_create",):
+        getattr(L, name).argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.kl_destroy.argtypes = [C.c_void_p]
+    L.kl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.kl_synchronize.argtypes = [C.c_void_p]
+    L.kl_set_pointer_mode.argtypes = [C.c_void_p, C.c_int]
+    L.kl_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.kl_get_option.argtypes = [C.c_void_p, C.c_int, _ip]
+    L.kl_comm_unique_id.argtypes = [C.c_void_p]
+    L.kl_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.kl_comm_rank.argtypes = [C.c_void_p, _ip, _ip]
+    L.kl_partition.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+    L.kl_apply_operator.argtypes = [C.c_void_p, C.POINTER(kl_operator_t), C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int]
+    L.kl_apply_precond.argtypes = [C.c_void_p, C.POINTER(kl_precond_t), C.POINTER(kl_operator_t),
+                                   C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, C.c_int]
+    gm = [C.c_void_p, C.POINTER(kl_operator_t), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+          C.c_double, _dp, _dp, _ip, _ip]
+    pc = [C.POINTER(kl_precond_t), _dp, C.c_int]
+    L.kl_gmres_mgsr_omp.argtypes = gm + pc
+    L.kl_gmres_mgsr_mf.argtypes = gm + pc
+    L.kl_gmres_hh_omp.argtypes = gm
+    L.kl_gmres_hh_prec_omp.argtypes = gm + pc
+    cg = [C.c_void_p, C.POINTER(kl_operator_t), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+          _ip, _dp]
+    for name in ("kl_cg", "kl_cg_omp", "kl_bicgstab"):
+        getattr(L, name).argtypes = cg
+    for name in ("kl_pcg", "kl_pcg_omp", "kl_pbicgstab", "kl_pbicgstab_omp"):
+        getattr(L, name).argtypes = cg + pc
+    L.kl_lanczos.argtypes = [C.c_void_p, C.POINTER(kl_operator_t), C.c_int, C.c_int, C.c_int, _dp, _dp]
+    L.kl_cheb_params_from_ritz.argtypes = [C.c_double, C.c_double, _dp]
+    L.kl_get_history.argtypes = [C.c_void_p, _dp, C.c_int, _ip]
+    L.kl_get_stats.argtypes = [C.c_void_p, C.POINTER(kl_stats_t)]
+    L.kl_vec_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.kl_vec_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.kl_vec_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.kl_vec_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    _lib = L
+    return L
+
+
+# --------------------------------------------------------------------------
+# plug-ins: the reference passes procedures; here they are descriptors
+# --------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Operator:
+    """procedure(stencil_vector) -- src/interfaces.f90:12-18."""
+    kind: int
+    eps_x: float = 1.0
+    eps_y: float = 1.0
+    fn: Optional[object] = None  # python callable(d_x:int, d_y:int, nx, ny_local, stream:int) for KL_OP_USER
+
+    def _c(self):
+        o = kl_operator_t()
+        o.kind, o.eps_x, o.eps_y = self.kind, self.eps_x, self.eps_y
+        keep = None
+        if self.kind == KL_OP_USER:
+            f = self.fn
+
+            def tramp(user, dx, dy, nx, nyl, stream):
+                try:
+                    f(dx, dy, nx, nyl, stream)
+                    return 0
+                except Exception:  # pragma: no cover
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+
+            keep = APPLY_FN(tramp)
+            o.fn = keep
+        return o, keep
+
+
+@dataclass(frozen=True)
+class Precond:
+    """procedure(precond) -- src/interfaces.f90:19-28."""
+    kind: int
+    degree: int = 0
+
+    def _c(self):
+        p = kl_precond_t()
+        p.kind, p.degree = self.kind, self.degree
+        return p
+
+
+stvec = Operator(KL_OP_POISSON5)                 # poisson::stvec        src/problems/poisson.f90:33
+stv_poisson = Operator(KL_OP_POISSON5_BRANCHY)   # poisson::stv_poisson  src/problems/poisson.f90:79
+cbpr2 = Precond(KL_PC_CBPR2)                     # chebyshev_precond::cbpr2  src/preconds/chebyshev.f90:8
+no_precond = Precond(KL_PC_NONE)
+
+
+def aniso(eps_x: float, eps_y: float) -> Operator:
+    return Operator(KL_OP_ANISO5, float(eps_x), float(eps_y))
+
+
+def cheb(degree: int) -> Precond:
+    return Precond(KL_PC_CHEB, int(degree))
+
+
+@dataclass
+class GmresResult:
+    x: object
+    final_err: np.ndarray
+    v_err: np.ndarray
+    n_out: int
+    restart_out: int          # restart_out / stages_out
+    status: int
+    history: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    stats: dict = field(default_factory=dict)
+
+
+@dataclass
+class CgResult:
+    x: object
+    iter: int
+    res: float
+    status: int
+    history: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    stats: dict = field(default_factory=dict)
+
+
+def _is_torch_cuda(a) -> bool:
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda") and a.is_cuda
+
+
+class Handle:
+    """kl_handle_t: one per GPU (one process per GPU for multi-GPU runs)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        rc = self._L.kl_create(C.byref(self._h), int(device))
+        if rc != 0:
+            raise KrylovError(f"kl_create(device={device}) failed with {rc}: no usable CUDA device "
+                              "(this library has no CPU path)")
+        self.device = int(device)
+        self.rank, self.nranks = 0, 1
+        if stream is not None:
+            self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream)))
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, allow=(0,)):
+        if rc not in allow:
+            msg = self._L.kl_last_error(self._h)
+            raise KrylovError(f"libkrylov_b200 error {rc}: {msg.decode() if msg else ''}")
+        return rc
+
+    def set_option(self, key: int, value: int):
+        self._chk(self._L.kl_set_option(self._h, key, int(value)))
+
+    def set_ortho(self, mode: int):
+        self.set_option(KL_OPT_ORTHO, mode)
+
+    def set_stream(self, stream: Optional[int]):
+        self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream or 0)))
+
+    def synchronize(self):
+        self._chk(self._L.kl_synchronize(self._h))
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), KL_UNIQUE_ID_BYTES)
+        self._chk(self._L.kl_comm_init(self._h, rank, nranks, buf))
+        self.rank, self.nranks = rank, nranks
+
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(KL_UNIQUE_ID_BYTES)
+        rc = self._L.kl_comm_unique_id(buf)
+        if rc != 0:
+            raise KrylovError(f"kl_comm_unique_id failed: {rc}")
+        return buf.raw
+
+    def partition(self, ny: int):
+        j0, nyl = C.c_int(), C.c_int()
+        self._chk(self._L.kl_partition(self._h, ny, C.byref(j0), C.byref(nyl)))
+        return j0.value, nyl.value
+
+    def stats(self) -> dict:
+        s = kl_stats_t()
+        self._chk(self._L.kl_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def history(self) -> np.ndarray:
+        n = C.c_int()
+        self._L.kl_get_history(self._h, None, 0, C.byref(n))
+        out = np.zeros(max(n.value, 1))
+        self._L.kl_get_history(self._h, out.ctypes.data_as(_dp), out.size, C.byref(n))
+        return out[: n.value]
+
+    # -- vector marshalling
+    def _in(self, a, n_expected=None):
+        if _is_torch_cuda(a):
+            import torch
+            assert a.dtype == torch.float64 and a.is_contiguous()
+            self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_DEVICE))
+            return a, C.c_void_p(a.data_ptr()), True
+        arr = np.ascontiguousarray(a, dtype=np.float64)
+        self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_HOST))
+        return arr, C.c_void_p(arr.ctypes.data), False
+
+    def _out_like(self, a, is_dev):
+        if is_dev:
+            import torch
+            o = torch.empty_like(a)
+            return o, C.c_void_p(o.data_ptr())
+        o = np.empty_like(a)
+        return o, C.c_void_p(o.ctypes.data)
+
+    @staticmethod
+    def _grid(b, nx, ny):
+        n = b.numel() if hasattr(b, "numel") else b.size
+        if nx is None:
+            # nsize = int(sqrt(real(n)))  (gmres_mgsr.f90:298) -- single precision sqrt
+            nx = ny = int(np.sqrt(np.float32(n)))
+        return int(nx), int(ny)
+
+    # -- operator / preconditioner application
+    def apply(self, A: Operator, x, nx: int, ny: int):
+        """call stvec(x, y, n)  (src/problems/poisson.f90:33)."""
+        xa, xp, dev = self._in(x)
+        y, yp = self._out_like(xa, dev)
+        o, keep = A._c()
+        self._chk(self._L.kl_apply_operator(self._h, C.byref(o), xp, yp, nx, ny))
+        return y
+
+    def apply_precond(self, M: Precond, A: Operator, r, params: Sequence[float], nx: int, ny: int):
+        """call cbpr2(A_x, r, z, aux, params, n)  (src/preconds/chebyshev.f90:8)."""
+        ra, rp, dev = self._in(r)
+        z, zp = self._out_like(ra, dev)
+        o, keep = A._c()
+        p = M._c()
+        pr = np.ascontiguousarray(params, dtype=np.float64)
+        self._chk(self._L.kl_apply_precond(self._h, C.byref(p), C.byref(o), rp, zp,
+                                           pr.ctypes.data_as(_dp), pr.size, nx, ny))
+        return z
+
+    # -- GMRES
+    def _gmres(self, fn, A, b, m, tol, M, params, nx, ny, with_pc=True):
+        ba, bp, dev = self._in(b)
+        nx, ny = self._grid(ba, nx, ny)
+        x, xp = self._out_like(ba, dev)
+        fe = np.zeros(m)
+        ve = np.zeros(m + 1)
+        n_out, rs = C.c_int(0), C.c_int(0)
+        o, keep = A._c()
+        args = [self._h, C.byref(o), bp, xp, nx, ny, int(m), float(tol), fe.ctypes.data_as(_dp),
+                ve.ctypes.data_as(_dp), C.byref(n_out), C.byref(rs)]
+        if with_pc:
+            p = (M or no_precond)._c()
+            pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
+            args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
+        rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        return GmresResult(x, fe, ve, n_out.value, rs.value, rc, self.history(), self.stats())
+
+    def gmres_mgsr_omp(self, Ax_vec, b, m, tol, M_inv=None, params=None, nx=None, ny=None):
+        return self._gmres(self._L.kl_gmres_mgsr_omp, Ax_vec, b, m, tol, M_inv, params, nx, ny)
+
+    def gmres_mgsr_mf(self, Ax_vec, b, m, tol, M_inv=None, params=None, nx=None, ny=None):
+        return self._gmres(self._L.kl_gmres_mgsr_mf, Ax_vec, b, m, tol, M_inv, params, nx, ny)
+
+    def gmres_hh_omp(self, Ax_vec, b, m, tol, nx=None, ny=None):
+        return self._gmres(self._L.kl_gmres_hh_omp, Ax_vec, b, m, tol, None, None, nx, ny, with_pc=False)
+
+    def gmres_hh_prec_omp(self, Ax_vec, b, m, tol, m_inv=None, params=None, nx=None, ny=None):
+        return self._gmres(self._L.kl_gmres_hh_prec_omp, Ax_vec, b, m, tol, m_inv, params, nx, ny)
+
+    # -- CG / BiCGSTAB
+    def _cg(self, fn, A, b, tol, it, M, params, nx, ny, with_pc):
+        ba, bp, dev = self._in(b)
+        nx, ny = self._grid(ba, nx, ny)
+        x, xp = self._out_like(ba, dev)
+        itc, res = C.c_int(int(it)), C.c_double(0.0)
+        o, keep = A._c()
+        args = [self._h, C.byref(o), bp, xp, nx, ny, float(tol), C.byref(itc), C.byref(res)]
+        if with_pc:
+            p = (M or no_precond)._c()
+            pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
+            args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
+        rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        return CgResult(x, itc.value, res.value, rc, self.history(), self.stats())
+
+    def cg(self, Ax_op, b, tol, iter, nx=None, ny=None):
+        return self._cg(self._L.kl_cg, Ax_op, b, tol, iter, None, None, nx, ny, False)
+
+    def cg_omp(self, Ax_op, b, tol, iter, nx=None, ny=None):
+        return self._cg(self._L.kl_cg_omp, Ax_op, b, tol, iter, None, None, nx, ny, False)
+
+    def pcg(self, Ax_op, b, tol, iter, M_inv, params, nx=None, ny=None):
+        return self._cg(self._L.kl_pcg, Ax_op, b, tol, iter, M_inv, params, nx, ny, True)
+
+    def pcg_omp(self, Ax_op, b, tol, iter, M_inv, params, nx=None, ny=None):
+        return self._cg(self._L.kl_pcg_omp, Ax_op, b, tol, iter, M_inv, params, nx, ny, True)
+
+    def bicgstab(self, ax_op, b, tol, iter, nx=None, ny=None):
+        return self._cg(self._L.kl_bicgstab, ax_op, b, tol, iter, None, None, nx, ny, False)
+
+    def pbicgstab(self, ax_op, b, tol, iter, m_inv, params, nx=None, ny=None):
+        return self._cg(self._L.kl_pbicgstab, ax_op, b, tol, iter, m_inv, params, nx, ny, True)
+
+    def pbicgstab_omp(self, ax_op, b, tol, max_iter, m_inv, params, nx=None, ny=None):
+        return self._cg(self._L.kl_pbicgstab_omp, ax_op, b, tol, max_iter, m_inv, params, nx, ny, True)
+
+    # -- Lanczos
+    def lanczos(self, A: Operator, nx: int, ny: int, steps: int = 30):
+        lo, hi = C.c_double(), C.c_double()
+        o, keep = A._c()
+        self._chk(self._L.kl_lanczos(self._h, C.byref(o), nx, ny, steps, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def cheb_params_from_ritz(self, theta_min: float, theta_max: float):
+        out = (C.c_double * 2)()
+        self._L.kl_cheb_params_from_ritz(theta_min, theta_max, out)
+        return (out[0], out[1])

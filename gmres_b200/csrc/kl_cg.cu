@@ -1,0 +1,199 @@
+// kl_cg.cu -- Conjugate Gradient, plain and left-preconditioned.
+//
+// Reference: src/cg.f90  cg :11-42, pcg :44-81, cg_omp :83-152, pcg_omp :154-234.
+// All four share one device implementation (the serial and OpenMP variants
+// compute the same quantities; only their summation order differs).
+//
+// Per iteration (fused path, built-in operator):
+//   K1  p' = z + beta*p ; ax = A p' ; ax.p'         reads z,p   writes p',ax   32n B
+//   K2  x += alpha p' ; r -= alpha ax ; r.r          reads x,p',r,ax writes x,r 48n B
+//   K3  (pcg) z = cbpr2(r) ; r.z                     reads r     writes z       16n B
+// alpha, beta, ||r||, the convergence flag and the residual history live on the
+// device; the host polls once every KL_OPT_CHECK_EVERY iterations.
+#include <math.h>
+
+#include "kl_ops.cuh"
+
+namespace kl {
+
+struct PostCgAlpha {  // cg.f90:124-126  alpha = rr / (ax.p)
+    double *S;
+    __device__ __forceinline__ void run() const {
+        S[S_PAP] = S[S_RED];
+        S[S_ALPHA] = S[S_RR] / S[S_RED];
+    }
+};
+
+struct PostCgEnd {
+    double *S;
+    int *I;
+    double *hist;
+    int hist_cap;
+    int precond;  // 0: S_RED[0] = r.r (cg.f90:135-138) ; 1: S_RED[0] = r.z, r.r in S_TMP0 (cg.f90:219-226)
+    __device__ __forceinline__ void run() const {
+        double num = S[S_RED];
+        double rr2 = precond ? S[S_TMP0] : num;
+        double res = sqrt(rr2);
+        S[S_BETA] = num / S[S_RR];
+        S[S_RR] = num;
+        S[S_RES] = res;
+        int it = I[I_ITER] + 1;
+        I[I_ITER] = it;
+        int hl = I[I_HIST];
+        if (hl < hist_cap) hist[hl] = res;
+        I[I_HIST] = hl + 1;
+        if (res < S[S_TOL]) I[I_CONV_AT] = it;          // cg.f90:144-149
+        else if (!(res == res)) { I[I_BREAKDOWN] = 1; I[I_CONV_AT] = it; }
+    }
+};
+
+static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+                    double tol, int *iter, double *res_out, const kl_precond_t *M, const double *params,
+                    int nparams) {
+    if (!c || !A || !b || !x || !iter || !res_out) return KL_ERR_INVALID;
+    Prob P;
+    KL_TRY(prob_init(&P, c, A, M, params, nparams, nx, ny));
+    const bool prec = P.pc.kind != KL_PC_NONE;
+    const bool fused = c->opt_fuse && P.builtin_op();
+    const size_t n = P.n;
+    const int maxit = *iter;
+    c->stats = kl_stats_t{};
+    cudaEvent_t evA, evB;
+    KL_CUDA(c, cudaEventCreate(&evA));
+    KL_CUDA(c, cudaEventCreate(&evB));
+    KL_CUDA(c, cudaEventRecord(evA, c->stream));
+
+    const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
+    const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0);
+    KL_TRY(ws_reserve(c, nvec * ws_need(n)));
+    ws_reset(c);
+    double *r = ws_take<double>(c, n), *p0 = ws_take<double>(c, n), *p1 = ws_take<double>(c, n);
+    double *ax = ws_take<double>(c, n);
+    double *dx = dev ? x : ws_take<double>(c, n);
+    double *z = r, *aux = nullptr, *aux2 = nullptr;
+    if (prec) {
+        z = ws_take<double>(c, n);
+        aux = ws_take<double>(c, n);
+        aux2 = ws_take<double>(c, n);
+    }
+    // x0 = 0 ; r0 = b ; p0 = r0 (cg.f90:102-108)
+    KL_TRY(stage_in(c, r, b, n));
+    KL_CUDA(c, cudaMemsetAsync(dx, 0, n * sizeof(double), c->stream));
+    KL_CUDA(c, cudaMemsetAsync(p0, 0, n * sizeof(double), c->stream));
+    KL_CUDA(c, cudaMemsetAsync(c->d_I, 0, sizeof(int) * I_COUNT, c->stream));
+    {
+        double S0[32] = {0};
+        S0[S_TOL] = tol;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_S, S0, sizeof S0, cudaMemcpyHostToDevice, c->stream));
+        int m1 = -1;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_I + I_CONV_AT, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    // rr = r.z  (z = M^-1 r for pcg, cg.f90:182 ; z = r otherwise)
+    if (prec) {
+        KL_TRY(pc_apply(&P, r, z, aux, aux2, 2, false, PostStoreRed{c->d_S, S_RR, 0}));
+    } else {
+        PDot2 d;
+        set_gate(d, c, false);
+        d.a = r; d.b = r; d.c = nullptr; d.d = nullptr;
+        KL_TRY(launch_pointwise(c, d, n, PostStoreRed{c->d_S, S_RR, 0}));
+    }
+    // S_BETA = 0 with p_old = 0 makes the first K1 produce p = z exactly.
+
+    KL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    double *pold = p0, *pnew = p1;
+    int done = 0, polls = 0;
+    int status = KL_NOT_CONVERGED;
+    while (done < maxit) {
+        int batch = c->opt_check_every;
+        if (batch > maxit - done) batch = maxit - done;
+        for (int k = 0; k < batch; ++k) {
+            // ---- K1
+            if (fused) {
+                Halo H;
+                const double *vecs[2] = {z, pold};
+                KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                FCgDir f;
+                set_io(f, &P, vecs, H);
+                set_gate(f, c, true);
+                f.p_new = pnew; f.ax = ax; f.S = c->d_S;
+                KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgAlpha{c->d_S}));
+            } else {
+                PAxpy u;
+                set_gate(u, c, true);
+                u.a = z; u.b = pold; u.y = pnew; u.S = c->d_S; u.s_idx = S_BETA; u.sign = 1.0;
+                KL_TRY(launch_pointwise(c, u, n, NoPost{}));
+                KL_TRY(op_apply(&P, pnew, ax, true));
+                PDot2 d;
+                set_gate(d, c, true);
+                d.a = ax; d.b = pnew; d.c = nullptr; d.d = nullptr;
+                KL_TRY(launch_pointwise(c, d, n, PostCgAlpha{c->d_S}));
+            }
+            // ---- K2
+            {
+                PCgUpdate u;
+                set_gate(u, c, true);
+                u.x = dx; u.r = r; u.p = pnew; u.ax = ax; u.S = c->d_S;
+                if (prec) KL_TRY(launch_pointwise(c, u, n, PostStoreRed{c->d_S, S_TMP0, 0}));
+                else KL_TRY(launch_pointwise(c, u, n, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}));
+            }
+            // ---- K3
+            if (prec)
+                KL_TRY(pc_apply(&P, r, z, aux, aux2, 2, true,
+                                PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 1}));
+            double *t = pold; pold = pnew; pnew = t;
+        }
+        done += batch;
+        KL_TRY(read_back(c));
+        ++polls;
+        if (c->h_pinned_i[I_CONV_AT] >= 0) {
+            status = c->h_pinned_i[I_BREAKDOWN] ? KL_BREAKDOWN : KL_OK;
+            break;
+        }
+    }
+    KL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    KL_TRY(stage_out(c, x, dx, n));
+    KL_TRY(fetch_history(c));
+    KL_CUDA(c, cudaEventRecord(evB, c->stream));
+    KL_CUDA(c, cudaStreamSynchronize(c->stream));
+    KL_CUDA(c, cudaGetLastError());
+    float ms = 0, ms_tot = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    cudaEventElapsedTime(&ms_tot, evA, evB);
+    cudaEventDestroy(evA);
+    cudaEventDestroy(evB);
+    const int its = c->h_pinned_i[I_ITER];
+    c->stats.iterations = its;
+    c->stats.cycles = polls;
+    c->stats.solve_ms = ms;
+    c->stats.total_ms = ms_tot;
+    c->stats.algorithmic_bytes = (double)its * (prec ? 96.0 : 80.0) * (double)n;
+    *res_out = c->h_pinned[S_RES];
+    if (status == KL_OK) *iter = c->h_pinned_i[I_CONV_AT];   // count on exit; unchanged if not converged
+    return status;
+}
+
+}  // namespace kl
+
+using namespace kl;
+
+extern "C" {
+
+int kl_cg(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny, double tol,
+          int *iter, double *res) {
+    return cg_solve(h, A, b, x, nx, ny, tol, iter, res, nullptr, nullptr, 0);
+}
+int kl_cg_omp(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+              double tol, int *iter, double *res) {
+    return cg_solve(h, A, b, x, nx, ny, tol, iter, res, nullptr, nullptr, 0);
+}
+int kl_pcg(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny, double tol,
+           int *iter, double *res, const kl_precond_t *M, const double *params, int nparams) {
+    return cg_solve(h, A, b, x, nx, ny, tol, iter, res, M, params, nparams);
+}
+int kl_pcg_omp(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+               double tol, int *iter, double *res, const kl_precond_t *M, const double *params,
+               int nparams) {
+    return cg_solve(h, A, b, x, nx, ny, tol, iter, res, M, params, nparams);
+}
+
+}  // extern "C"

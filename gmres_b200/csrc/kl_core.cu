@@ -1,0 +1,365 @@
+// kl_core.cu -- handle lifecycle, options, workspace, device vectors, NCCL plumbing.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "kl_internal.cuh"
+
+namespace kl {
+
+int ws_reserve(Ctx *c, size_t bytes) {
+    if (bytes <= c->ws_bytes) return KL_OK;
+    if (c->ws) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->ws);
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&c->ws, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return c->fail(KL_ERR_ALLOC, "workspace cudaMalloc", e);
+    }
+    c->ws_bytes = bytes;
+    return KL_OK;
+}
+
+// ------------------------------------------------------------------------
+// NCCL, loaded at run time (dlopen) so that the library has no link-time
+// dependency on it: single-GPU users and CPU-only symbol checks never need it,
+// and under torchrun the process-wide libnccl.so.2 that torch already loaded is
+// the one that gets used.
+// ------------------------------------------------------------------------
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_p;
+enum { kNcclFloat64 = 8, kNcclSum = 0 };
+struct Nccl {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+    int (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_p) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load(std::string *err) {
+    if (g_nccl.lib) return KL_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void *lib = nullptr;
+    const char *env = getenv("KL_NCCL_LIB");
+    if (env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (int i = 0; !lib && names[i]; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        if (err) *err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return KL_ERR_NCCL;
+    }
+#define KL_SYM(field, name)                                            \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                      \
+    if (!g_nccl.field) {                                               \
+        if (err) *err = std::string("missing NCCL symbol ") + name;    \
+        return KL_ERR_NCCL;                                            \
+    }
+    KL_SYM(GetUniqueId, "ncclGetUniqueId")
+    KL_SYM(CommInitRank, "ncclCommInitRank")
+    KL_SYM(CommDestroy, "ncclCommDestroy")
+    KL_SYM(AllReduce, "ncclAllReduce")
+    KL_SYM(Send, "ncclSend")
+    KL_SYM(Recv, "ncclRecv")
+    KL_SYM(GroupStart, "ncclGroupStart")
+    KL_SYM(GroupEnd, "ncclGroupEnd")
+    KL_SYM(GetErrorString, "ncclGetErrorString")
+#undef KL_SYM
+    g_nccl.lib = lib;
+    return KL_OK;
+}
+
+#define KL_NCCL(c, call)                                                                   \
+    do {                                                                                   \
+        int r__ = (call);                                                                  \
+        if (r__ != 0) {                                                                    \
+            (c)->err = std::string(#call ": ") + g_nccl.GetErrorString(r__);               \
+            return KL_ERR_NCCL;                                                            \
+        }                                                                                  \
+    } while (0)
+
+int comm_allreduce(Ctx *c, double *d_buf, int count) {
+    if (c->nranks == 1) return KL_OK;
+    KL_NCCL(c, g_nccl.AllReduce(d_buf, d_buf, (size_t)count, kNcclFloat64, kNcclSum,
+                                (ncclComm_p)c->nccl_comm, c->stream));
+    return KL_OK;
+}
+
+// Exchange the boundary lines of `nvec` slab vectors with the neighbour ranks.
+// send_lo_rows[v] = this rank's first line, goes to rank-1's `hi` halo;
+// send_hi_rows[v] = this rank's last line, goes to rank+1's `lo` halo.
+int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *const *send_hi_rows,
+                       double *const *recv_lo, double *const *recv_hi, int nvec, int nx) {
+    if (c->nranks == 1) return KL_OK;
+    ncclComm_p comm = (ncclComm_p)c->nccl_comm;
+    KL_NCCL(c, g_nccl.GroupStart());
+    for (int v = 0; v < nvec; ++v) {
+        if (c->rank > 0) {
+            KL_NCCL(c, g_nccl.Send(send_lo_rows[v], nx, kNcclFloat64, c->rank - 1, comm, c->stream));
+            KL_NCCL(c, g_nccl.Recv(recv_lo[v], nx, kNcclFloat64, c->rank - 1, comm, c->stream));
+        }
+        if (c->rank < c->nranks - 1) {
+            KL_NCCL(c, g_nccl.Send(send_hi_rows[v], nx, kNcclFloat64, c->rank + 1, comm, c->stream));
+            KL_NCCL(c, g_nccl.Recv(recv_hi[v], nx, kNcclFloat64, c->rank + 1, comm, c->stream));
+        }
+    }
+    KL_NCCL(c, g_nccl.GroupEnd());
+    return KL_OK;
+}
+
+}  // namespace kl
+
+using namespace kl;
+
+extern "C" {
+
+int kl_version(void) { return KL_VERSION; }
+
+int kl_create(kl_handle_t *h, int device) {
+    if (!h) return KL_ERR_INVALID;
+    *h = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return KL_ERR_CUDA;  // fail loudly: there is no CPU fallback
+    }
+    if (device < 0 || device >= ndev) return KL_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return KL_ERR_CUDA;
+    Ctx *c = new Ctx();
+    c->device = device;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_S, sizeof(double) * S_COUNT) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_I, sizeof(int) * I_COUNT) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxCols * kMaxBlocks / 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_counter, sizeof(unsigned) * 16) == cudaSuccess;
+    c->hist_cap = 1 << 20;
+    ok = ok && cudaMalloc(&c->d_hist, sizeof(double) * c->hist_cap) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_pinned, sizeof(double) * S_COUNT) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_pinned_i, sizeof(int) * I_COUNT) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemset(c->d_S, 0, sizeof(double) * S_COUNT) == cudaSuccess &&
+             cudaMemset(c->d_I, 0, sizeof(int) * I_COUNT) == cudaSuccess &&
+             cudaMemset(c->d_counter, 0, sizeof(unsigned) * 16) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        kl_destroy(c);
+        return KL_ERR_ALLOC;
+    }
+    *h = c;
+    return KL_OK;
+}
+
+int kl_destroy(kl_handle_t h) {
+    if (!h) return KL_OK;
+    Ctx *c = h;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)c->nccl_comm);
+    cudaFree(c->d_S);
+    cudaFree(c->d_I);
+    cudaFree(c->d_partials);
+    cudaFree(c->d_counter);
+    cudaFree(c->d_hist);
+    cudaFree(c->ws);
+    cudaFree(c->d_halo);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_pinned_i) cudaFreeHost(c->h_pinned_i);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return KL_OK;
+}
+
+const char *kl_last_error(kl_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int kl_set_stream(kl_handle_t h, void *cuda_stream) {
+    if (!h) return KL_ERR_INVALID;
+    Ctx *c = h;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+        c->own_stream = false;
+    } else {
+        KL_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return KL_OK;
+}
+
+int kl_synchronize(kl_handle_t h) {
+    if (!h) return KL_ERR_INVALID;
+    KL_CUDA(h, cudaStreamSynchronize(h->stream));
+    return KL_OK;
+}
+
+int kl_set_pointer_mode(kl_handle_t h, int mode) {
+    if (!h || (mode != KL_POINTER_HOST && mode != KL_POINTER_DEVICE)) return KL_ERR_INVALID;
+    h->pointer_mode = mode;
+    return KL_OK;
+}
+
+int kl_set_option(kl_handle_t h, int key, int value) {
+    if (!h) return KL_ERR_INVALID;
+    switch (key) {
+        case KL_OPT_ORTHO:
+            if (value < KL_ORTHO_MGS2 || value > KL_ORTHO_CGS2_SELECTIVE) return KL_ERR_INVALID;
+            h->opt_ortho = value;
+            break;
+        case KL_OPT_MAX_RESTARTS:
+            if (value < 1) return KL_ERR_INVALID;
+            h->opt_max_restarts = value;
+            break;
+        case KL_OPT_VERR: h->opt_verr = value != 0; break;
+        case KL_OPT_CHECK_EVERY:
+            if (value < 1) return KL_ERR_INVALID;
+            h->opt_check_every = value;
+            break;
+        case KL_OPT_USE_GRAPH: h->opt_use_graph = value != 0; break;
+        case KL_OPT_HH_MODE:
+            if (value != KL_HH_SEQUENTIAL && value != KL_HH_BLOCKED) return KL_ERR_INVALID;
+            h->opt_hh_mode = value;
+            break;
+        case KL_OPT_FUSE: h->opt_fuse = value != 0; break;
+        default: return KL_ERR_INVALID;
+    }
+    return KL_OK;
+}
+
+int kl_get_option(kl_handle_t h, int key, int *value) {
+    if (!h || !value) return KL_ERR_INVALID;
+    switch (key) {
+        case KL_OPT_ORTHO: *value = h->opt_ortho; break;
+        case KL_OPT_MAX_RESTARTS: *value = h->opt_max_restarts; break;
+        case KL_OPT_VERR: *value = h->opt_verr; break;
+        case KL_OPT_CHECK_EVERY: *value = h->opt_check_every; break;
+        case KL_OPT_USE_GRAPH: *value = h->opt_use_graph; break;
+        case KL_OPT_HH_MODE: *value = h->opt_hh_mode; break;
+        case KL_OPT_FUSE: *value = h->opt_fuse; break;
+        default: return KL_ERR_INVALID;
+    }
+    return KL_OK;
+}
+
+// ---- communicator -------------------------------------------------------
+int kl_comm_unique_id(void *id_out) {
+    if (!id_out) return KL_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId_t) == KL_UNIQUE_ID_BYTES, "NCCL unique id size");
+    std::string err;
+    if (nccl_load(&err) != KL_OK) return KL_ERR_NCCL;
+    ncclUniqueId_t id;
+    if (g_nccl.GetUniqueId(&id) != 0) return KL_ERR_NCCL;
+    memcpy(id_out, &id, sizeof id);
+    return KL_OK;
+}
+
+int kl_comm_init(kl_handle_t h, int rank, int nranks, const void *id_bytes) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks) return KL_ERR_INVALID;
+    Ctx *c = h;
+    if (nranks == 1) {
+        c->rank = 0;
+        c->nranks = 1;
+        return KL_OK;
+    }
+    if (!id_bytes) return KL_ERR_INVALID;
+    if (nccl_load(&c->err) != KL_OK) return KL_ERR_NCCL;
+    KL_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId_t id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclComm_p comm = nullptr;
+    KL_NCCL(c, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->nccl_comm = comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    return KL_OK;
+}
+
+int kl_comm_rank(kl_handle_t h, int *rank, int *nranks) {
+    if (!h) return KL_ERR_INVALID;
+    if (rank) *rank = h->rank;
+    if (nranks) *nranks = h->nranks;
+    return KL_OK;
+}
+
+int kl_partition(kl_handle_t h, int ny, int *j0, int *ny_local) {
+    if (!h || ny < 1) return KL_ERR_INVALID;
+    // contiguous lines, the first (ny % P) ranks get one extra line
+    const int P = h->nranks, p = h->rank;
+    const int base = ny / P, rem = ny % P;
+    const int start = p * base + (p < rem ? p : rem);
+    const int cnt = base + (p < rem ? 1 : 0);
+    if (j0) *j0 = start;
+    if (ny_local) *ny_local = cnt;
+    return KL_OK;
+}
+
+// ---- device vectors -------------------------------------------------------
+int kl_vec_alloc(kl_handle_t h, size_t n, double **d_ptr) {
+    if (!h || !d_ptr) return KL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMalloc((void **)d_ptr, n * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return h->fail(KL_ERR_ALLOC, "kl_vec_alloc", e);
+    }
+    return KL_OK;
+}
+int kl_vec_free(kl_handle_t h, double *d_ptr) {
+    if (!h) return KL_ERR_INVALID;
+    cudaStreamSynchronize(h->stream);
+    KL_CUDA(h, cudaFree(d_ptr));
+    return KL_OK;
+}
+int kl_vec_upload(kl_handle_t h, double *d_dst, const double *h_src, size_t n) {
+    if (!h) return KL_ERR_INVALID;
+    KL_CUDA(h, cudaMemcpyAsync(d_dst, h_src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KL_CUDA(h, cudaStreamSynchronize(h->stream));
+    return KL_OK;
+}
+int kl_vec_download(kl_handle_t h, double *h_dst, const double *d_src, size_t n) {
+    if (!h) return KL_ERR_INVALID;
+    KL_CUDA(h, cudaMemcpyAsync(h_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KL_CUDA(h, cudaStreamSynchronize(h->stream));
+    return KL_OK;
+}
+
+int kl_get_history(kl_handle_t h, double *out, int cap, int *len) {
+    if (!h) return KL_ERR_INVALID;
+    if (len) *len = h->history_len;
+    if (out && cap > 0) {
+        int k = h->history_len < cap ? h->history_len : cap;
+        if (k > (int)h->history.size()) k = (int)h->history.size();
+        memcpy(out, h->history.data(), sizeof(double) * k);
+    }
+    return KL_OK;
+}
+
+int kl_get_stats(kl_handle_t h, kl_stats_t *out) {
+    if (!h || !out) return KL_ERR_INVALID;
+    *out = h->stats;
+    return KL_OK;
+}
+
+int kl_cheb_params_from_ritz(double theta_min, double theta_max, double params_out[2]) {
+    (void)theta_min;
+    if (!params_out || !(theta_max > 0)) return KL_ERR_INVALID;
+    // tests/test_poisson_mf.f90:38 passes (8.2, 0.2) for a spectrum whose top is 8:
+    // (1.025 lambda_max, 1.025 lambda_max / 41), "max first".
+    params_out[0] = 1.025 * theta_max;
+    params_out[1] = params_out[0] / 41.0;
+    return KL_OK;
+}
+
+}  // extern "C"

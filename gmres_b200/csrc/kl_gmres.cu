@@ -1,0 +1,722 @@
+// kl_gmres.cu -- restarted, left-preconditioned GMRES(m) with Gram-Schmidt
+// orthogonalisation applied twice.
+//
+// Reference: src/gmres_mgsr.f90  gmres_mgsr_omp :277-421, gmres_mgsr_mf :98-199.
+//
+// Data layout in HBM: the Krylov basis V is n x (m+1) column-major with leading
+// dimension ldv >= n (each basis vector contiguous, 256-byte aligned); H is
+// (m+1) x m column-major; g, cs, sn, y, final_err are small device arrays.
+//
+// One Arnoldi step (fused path):
+//   stencil      V_j = w/h_val ; z = A V_j          (FScaleApply, 24n B)
+//   stencil      w = cbpr2(z)                        (FCbpr2, 16n B)
+//   k_vtw        h1 = V(:,0..j)^T w                  (8n(j+1) + 8n B)     |
+//   k_wmvh       w -= V h1                           (8n(j+1) + 16n B)    | CGS2
+//   k_vtw        h2 = V^T w ; H(:,j) = h1 + h2       (8n(j+1) + 8n B)     |
+//   k_wmvh       w -= V h2 ; ||w||^2 ; Givens        (8n(j+1) + 16n B)    |
+// or, with KL_ORTHO_MGS2, the reference's 2(j+1) sequential dot/axpy pairs
+// (k_mgs_step: axpy with the previous column fused with the dot of the next).
+// The Givens update, the residual estimate, n_out, the convergence flag and the
+// residual history are produced on the device by one warp (givens_update_warp);
+// the host reads them once per restart cycle.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "kl_ops.cuh"
+
+namespace kl {
+
+constexpr int kTsThreads = 256;
+constexpr int kTsWarps = kTsThreads / 32;
+constexpr int kTsCpw = 12;          // columns per warp per pass
+constexpr int kTsU = 4;             // row chunks per lane per trip
+constexpr int kTsMaxBlocks = 1024;  // partials leading dimension
+
+struct GmresDev {
+    double *H;      // (m+1) x m, ldh = m+1
+    double *g, *cs, *sn, *y, *fe, *hvec;
+    double *S;
+    int *I;
+    double *hist;
+    int hist_cap;
+    int m, ldh;
+    int mf;         // 1: gmres_mgsr_mf semantics (h_val < tol also stops; :172)
+};
+
+// ---- Givens update by ONE WARP (gmres_mgsr.f90:362-389) --------------------
+// sumsq = ||w||^2 after orthogonalisation.  Called by warp 0 of the last block
+// of the final update kernel (single GPU) or by k_givens (multi GPU).
+__device__ __forceinline__ void givens_update_warp(const GmresDev &G, int j, double sumsq, int lane,
+                                                   double *sm /* 3*(m+2) doubles */) {
+    double *sh = sm, *sc = sm + (G.m + 2), *ss = sm + 2 * (G.m + 2);
+    double *Hj = G.H + (size_t)j * G.ldh;
+    for (int i = lane; i <= j; i += 32) sh[i] = Hj[i];
+    for (int i = lane; i < j; i += 32) {
+        sc[i] = G.cs[i];
+        ss[i] = G.sn[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double h_val = sqrt(sumsq);                 // :362 norm2(w)
+        double hi = sh[0];
+        for (int i = 0; i < j; ++i) {                     // :365-369
+            const double hn = sh[i + 1], c = sc[i], s = ss[i];
+            Hj[i] = fma(c, hi, s * hn);
+            hi = fma(-s, hi, c * hn);
+        }
+        // hi = H(j,j) after the previous rotations; H(j+1,j) = h_val (:363)
+        const double hjj = hi, hj1 = h_val;
+        double ds = hypot(hj1, hjj);                      // :370
+        double c = hjj / ds, s = hj1 / ds;                // :371-372
+        G.cs[j] = c;
+        G.sn[j] = s;
+        Hj[j] = fma(c, hjj, s * hj1);                     // :373
+        Hj[j + 1] = 0.0;                                  // :374
+        double tmp = G.g[j], gn = G.g[j + 1];             // :378-380
+        G.g[j] = fma(c, tmp, s * gn);
+        double gj1 = fma(-s, tmp, c * gn);
+        G.g[j + 1] = gj1;
+        double fe = fabs(gj1) / G.S[S_BETA0];             // :383
+        G.fe[j] = fe;
+        G.S[S_HVAL] = h_val;
+        G.S[S_RES] = fe;
+        int hl = G.I[I_HIST];
+        if (hl < G.hist_cap) G.hist[hl] = fe;
+        G.I[I_HIST] = hl + 1;
+        G.I[I_ITER] = G.I[I_ITER] + 1;
+        G.I[I_NOUT] = j + 1;                              // :389
+        const double tol = G.S[S_TOL];
+        bool conv = G.mf ? (h_val < tol || fe < tol) : (fe < tol);   // :172 / :385
+        if (!(fe == fe)) { G.I[I_BREAKDOWN] = 1; conv = true; }
+        if (conv) G.I[I_CONV_AT] = j;
+    }
+}
+
+__global__ void k_givens(const GmresDev G, const int j) {
+    extern __shared__ double sm[];
+    if (G.I[I_CONV_AT] >= 0) return;
+    givens_update_warp(G, j, G.S[S_RED], threadIdx.x, sm);
+}
+
+// H(0..ncols-1, j) (+)= hvec   (gmres_mgsr.f90:351-353)
+__global__ void k_hacc(const GmresDev G, const int j, const int ncols, const int accumulate) {
+    if (G.I[I_CONV_AT] >= 0) return;
+    double *Hj = G.H + (size_t)j * G.ldh;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x)
+        Hj[c] = accumulate ? Hj[c] + G.hvec[c] : G.hvec[c];
+}
+
+// ---- tall-skinny projection  out[c] = V(:,c) . w , c < ncols ------------------
+// 8 warps per block arranged as RG row groups x CG column groups.  A warp keeps
+// up to kTsCpw accumulators and streams its columns; w is read once per block
+// trip (L1-shared between the column-group warps).  Deterministic two-stage
+// reduction: block partials [col][block] -> last block sums over blocks.
+template <int VEC>
+__global__ void __launch_bounds__(kTsThreads, 2)
+k_vtw(const double *__restrict__ V, const size_t ldv, const double *__restrict__ w, const size_t n,
+      const int ncols, double *__restrict__ partials, unsigned int *counter, double *__restrict__ out,
+      const GmresDev G, const int j, const int h_mode /* 0: none, 1: H=out, 2: H+=out */,
+      const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    __shared__ double s_part[kTsWarps][kTsCpw];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int ncg = (ncols + kTsCpw - 1) / kTsCpw;
+    int CG = 1;
+    while (CG < ncg && CG < kTsWarps) CG <<= 1;
+    const int RG = kTsWarps / CG;
+    const int cg = wid % CG, rg = wid / CG;
+    constexpr size_t WROWS = (size_t)32 * kTsU * VEC;   // rows per warp trip
+    const size_t TR = WROWS * RG;                       // rows per block trip
+    const int cols_per_pass = CG * kTsCpw;
+    for (int cbase = 0; cbase < ncols; cbase += cols_per_pass) {
+        const int c0 = cbase + cg * kTsCpw;
+        double acc[kTsCpw];
+#pragma unroll
+        for (int c = 0; c < kTsCpw; ++c) acc[c] = 0.0;
+        for (size_t t0 = (size_t)blockIdx.x * TR; t0 < n; t0 += (size_t)gridDim.x * TR) {
+            const size_t r0 = t0 + (size_t)rg * WROWS + (size_t)lane * VEC;
+            double wv[kTsU][VEC];
+#pragma unroll
+            for (int u = 0; u < kTsU; ++u) {
+                const size_t r = r0 + (size_t)u * 32 * VEC;
+                if (r < n) {
+                    if (VEC == 2) {
+                        double2 t = ldg2(w + r);
+                        wv[u][0] = t.x; wv[u][VEC - 1] = t.y;
+                    } else {
+                        wv[u][0] = __ldg(w + r);
+                    }
+                } else {
+                    wv[u][0] = 0.0; wv[u][VEC - 1] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kTsCpw; ++c) {
+                if (c0 + c < ncols) {
+                    const double *col = V + (size_t)(c0 + c) * ldv;
+#pragma unroll
+                    for (int u = 0; u < kTsU; ++u) {
+                        const size_t r = r0 + (size_t)u * 32 * VEC;
+                        if (r < n) {
+                            if (VEC == 2) {
+                                double2 t = ldg2(col + r);
+                                acc[c] = fma(t.x, wv[u][0], acc[c]);
+                                acc[c] = fma(t.y, wv[u][VEC - 1], acc[c]);
+                            } else {
+                                acc[c] = fma(__ldg(col + r), wv[u][0], acc[c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kTsCpw; ++c) {
+            double s = warp_sum(acc[c]);
+            if (lane == 0) s_part[wid][c] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < cols_per_pass) {
+            const int col = cbase + threadIdx.x;
+            if (col < ncols) {
+                const int g = threadIdx.x / kTsCpw, c = threadIdx.x % kTsCpw;
+                double s = 0.0;
+                for (int r = 0; r < RG; ++r) s += s_part[r * CG + g][c];
+                partials[(size_t)col * kTsMaxBlocks + blockIdx.x] = s;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- grid stage
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned prev = atomicAdd(counter, 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int col = wid; col < ncols; col += kTsWarps) {
+        const volatile double *p = partials + (size_t)col * kTsMaxBlocks;
+        double s = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += p[b];
+        s = warp_sum(s);
+        if (lane == 0) {
+            out[col] = s;
+            if (h_mode) {
+                double *Hj = G.H + (size_t)j * G.ldh;
+                Hj[col] = (h_mode == 2) ? Hj[col] + s : s;
+            }
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+// ---- w_out = w - V(:,0..ncols-1) h  (+ ||w_out||^2, + Givens in the last block) --
+// FMA order = column order (the CPU twin's CGS2 loop).
+template <int VEC>
+__global__ void __launch_bounds__(kTsThreads)
+k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n, const int ncols,
+       const double *__restrict__ h, const RedCtl rc, const int want_norm, const GmresDev G,
+       const int j, const int fuse_givens, const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    extern __shared__ double sm[];   // max(ncols, 3*(m+2)) doubles + reduction scratch
+    double *sh = sm;
+    for (int c = threadIdx.x; c < ncols; c += kTsThreads) sh[c] = h[c];
+    __syncthreads();
+    double nacc = 0.0;
+    const size_t nchunk = n / VEC;
+    for (size_t ch = (size_t)blockIdx.x * kTsThreads + threadIdx.x; ch < nchunk;
+         ch += (size_t)gridDim.x * kTsThreads) {
+        const size_t r = ch * VEC;
+        double a[VEC];
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(w + r);
+            a[0] = t.x; a[VEC - 1] = t.y;
+        } else {
+            a[0] = w[r];
+        }
+        int c = 0;
+        for (; c + 8 <= ncols; c += 8) {
+            double v[8][VEC];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double *col = V + (size_t)(c + q) * ldv + r;
+                if (VEC == 2) {
+                    double2 t = ldg2(col);
+                    v[q][0] = t.x; v[q][VEC - 1] = t.y;
+                } else {
+                    v[q][0] = __ldg(col);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double hq = -sh[c + q];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) a[e] = fma(hq, v[q][e], a[e]);
+            }
+        }
+        for (; c < ncols; ++c) {
+            const double *col = V + (size_t)c * ldv + r;
+            const double hq = -sh[c];
+            if (VEC == 2) {
+                double2 t = ldg2(col);
+                a[0] = fma(hq, t.x, a[0]);
+                a[VEC - 1] = fma(hq, t.y, a[VEC - 1]);
+            } else {
+                a[0] = fma(hq, __ldg(col), a[0]);
+            }
+        }
+        if (VEC == 2) stg2(w + r, a[0], a[VEC - 1]);
+        else w[r] = a[0];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) nacc = fma(a[e], a[e], nacc);
+    }
+    if (!want_norm) return;
+    __syncthreads();
+    __shared__ double s_red[kTsWarps];
+    __shared__ int s_flag;
+    double accv[1] = {nacc};
+    block_sum<1, kTsThreads>(accv, s_red);
+    if (grid_sum<1>(accv, rc, gridDim.x, blockIdx.x, &s_flag)) {
+        if (fuse_givens && threadIdx.x < 32) givens_update_warp(G, j, rc.red[0], threadIdx.x, sm);
+    }
+}
+
+// ---- faithful MGS step (gmres_mgsr.f90:342-359), two loops fused in one pass:
+//   w -= h_prev * V_prev   (skipped when V_prev == nullptr)
+//   acc = V_cur . w        (skipped when V_cur == nullptr; then acc = ||w||^2 if want_norm)
+// post (last block): h = acc ; H(i_cur, j) += h ; S_TMP0 = h
+struct PMgsStep : PwBase<1> {
+    double *w;
+    const double *vprev, *vcur;
+    const double *S;
+    double hprev;
+    int want_norm;
+    __device__ __forceinline__ void init() { hprev = vprev ? S[S_TMP0] : 0.0; }
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *acc) const {
+        double a[VEC];
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(w + i);
+            a[0] = t.x; a[VEC - 1] = t.y;
+        } else {
+            a[0] = w[i];
+        }
+        if (vprev) {
+            double p[VEC];
+            KL_LD(VEC, p, vprev, i)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a[e] = fma(-hprev, p[e], a[e]);
+            KL_ST(VEC, w, i, a)
+        }
+        if (vcur) {
+            double q[VEC];
+            KL_LD(VEC, q, vcur, i)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], q[e], acc[0]);
+        } else if (want_norm) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], a[e], acc[0]);
+        }
+    }
+};
+struct PostMgs {
+    GmresDev G;
+    int j, i_cur;
+    __device__ __forceinline__ void run() const {
+        double h = G.S[S_RED];
+        G.S[S_TMP0] = h;
+        double *Hj = G.H + (size_t)j * G.ldh;
+        Hj[i_cur] = Hj[i_cur] + h;
+    }
+};
+struct PostBeta {   // gmres_mgsr.f90:322-323  beta = norm2(w) ; g(1) = beta
+    GmresDev G;
+    __device__ __forceinline__ void run() const {
+        double beta = sqrt(G.S[S_RED]);
+        G.S[S_NORM] = beta;
+        G.g[0] = beta;
+    }
+};
+
+// ---- back substitution by one warp (gmres_mgsr.f90:394-398) -------------------
+// lane 0 runs the reference's sequential recurrence; the warp stages row i of H.
+__global__ void k_backsolve(const GmresDev G) {
+    extern __shared__ double sm[];   // m doubles row + m doubles y
+    const int lane = threadIdx.x;
+    const int n_out = G.I[I_NOUT];
+    double *row = sm, *ys = sm + G.m;
+    for (int i = lane; i < G.m; i += 32) ys[i] = 0.0;
+    __syncwarp();
+    for (int i = n_out - 1; i >= 0; --i) {
+        for (int k = i + lane; k < n_out; k += 32) row[k] = G.H[(size_t)k * G.ldh + i];
+        __syncwarp();
+        if (lane == 0) {
+            double s = 0.0;
+            for (int k = i + 1; k < n_out; ++k) s = fma(row[k], ys[k], s);
+            ys[i] = (G.g[i] - s) / row[i];
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < G.m; i += 32) G.y[i] = ys[i];
+}
+
+// ---- x += V(:,0..n_out-1) y   (gmres_mgsr.f90:400-406) -------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kTsThreads)
+k_xpvy(const double *__restrict__ V, const size_t ldv, double *x, const size_t n, const GmresDev G) {
+    extern __shared__ double sy[];
+    const int n_out = G.I[I_NOUT];
+    for (int c = threadIdx.x; c < n_out; c += kTsThreads) sy[c] = G.y[c];
+    __syncthreads();
+    const size_t nchunk = n / VEC;
+    for (size_t ch = (size_t)blockIdx.x * kTsThreads + threadIdx.x; ch < nchunk;
+         ch += (size_t)gridDim.x * kTsThreads) {
+        const size_t r = ch * VEC;
+        double s[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s[e] = 0.0;
+        int c = 0;
+        for (; c + 8 <= n_out; c += 8) {
+            double v[8][VEC];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double *col = V + (size_t)(c + q) * ldv + r;
+                if (VEC == 2) {
+                    double2 t = ldg2(col);
+                    v[q][0] = t.x; v[q][VEC - 1] = t.y;
+                } else {
+                    v[q][0] = __ldg(col);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s[e] = fma(v[q][e], sy[c + q], s[e]);
+        }
+        for (; c < n_out; ++c) {
+            const double *col = V + (size_t)c * ldv + r;
+            if (VEC == 2) {
+                double2 t = ldg2(col);
+                s[0] = fma(t.x, sy[c], s[0]);
+                s[VEC - 1] = fma(t.y, sy[c], s[VEC - 1]);
+            } else {
+                s[0] = fma(__ldg(col), sy[c], s[0]);
+            }
+        }
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(x + r);
+            stg2(x + r, t.x + s[0], t.y + s[VEC - 1]);
+        } else {
+            x[r] = x[r] + s[0];
+        }
+    }
+}
+
+static inline int ts_grid(size_t n, int vec) {
+    size_t rows_per_block = (size_t)32 * kTsU * vec;  // at least one warp trip
+    size_t b = (n + rows_per_block - 1) / rows_per_block;
+    size_t cap = (size_t)kNumSM * 2;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+static inline int upd_grid(size_t nchunk) {
+    size_t b = (nchunk + kTsThreads - 1) / kTsThreads;
+    size_t cap = (size_t)kNumSM * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int launch_vtw(Ctx *c, const double *V, size_t ldv, const double *w, size_t n, int ncols, double *out,
+               const GmresDev &G, int j, int h_mode, bool gated) {
+    const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
+    const int grid = ts_grid(n, vec);
+    const int hm = c->nranks == 1 ? h_mode : 0;
+    if (vec == 2)
+        k_vtw<2><<<grid, kTsThreads, 0, c->stream>>>(V, ldv, w, n, ncols, c->d_partials, c->d_counter + 1,
+                                                     out, G, j, hm, gated ? c->d_I : nullptr);
+    else
+        k_vtw<1><<<grid, kTsThreads, 0, c->stream>>>(V, ldv, w, n, ncols, c->d_partials, c->d_counter + 1,
+                                                     out, G, j, hm, gated ? c->d_I : nullptr);
+    c->stats.kernel_launches++;
+    if (c->nranks > 1) {
+        KL_TRY(comm_allreduce(c, out, ncols));
+        if (h_mode) {
+            k_hacc<<<1, 128, 0, c->stream>>>(G, j, ncols, h_mode == 2);
+            c->stats.kernel_launches++;
+        }
+    }
+    return KL_OK;
+}
+
+int launch_wmvh(Ctx *c, const double *V, size_t ldv, double *w, size_t n, int ncols, const double *h,
+                bool want_norm, const GmresDev &G, int j, bool givens, bool gated) {
+    const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
+    const int grid = upd_grid(n / vec);
+    const size_t smem = sizeof(double) * std::max(ncols + 8, 3 * (G.m + 2));
+    const int fuse = (givens && c->nranks == 1) ? 1 : 0;
+    RedCtl rc = redctl(c);
+    if (vec == 2)
+        k_wmvh<2><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, want_norm, G, j, fuse,
+                                                         gated ? c->d_I : nullptr);
+    else
+        k_wmvh<1><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, want_norm, G, j, fuse,
+                                                         gated ? c->d_I : nullptr);
+    c->stats.kernel_launches++;
+    if (want_norm && c->nranks > 1) {
+        KL_TRY(comm_allreduce(c, c->d_S + S_RED, 1));
+        if (givens) {
+            k_givens<<<1, 32, sizeof(double) * 3 * (G.m + 2), c->stream>>>(G, j);
+            c->stats.kernel_launches++;
+        }
+    }
+    return KL_OK;
+}
+
+// Gram-matrix epilogue shared with the Householder solver: G[c*(k)+i] = V_i . V_c, i <= c
+int gram_lower(Ctx *c, const double *V, size_t ldv, size_t n, int k, double *d_gram, std::vector<double> &out) {
+    GmresDev none{};
+    for (int col = 0; col < k; ++col)
+        KL_TRY(launch_vtw(c, V, ldv, V + (size_t)col * ldv, n, col + 1, d_gram + (size_t)col * k, none, 0, 0, false));
+    out.assign((size_t)k * k, 0.0);
+    KL_CUDA(c, cudaMemcpyAsync(out.data(), d_gram, sizeof(double) * k * k, cudaMemcpyDeviceToHost, c->stream));
+    KL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KL_OK;
+}
+
+static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+                            int m, double tol, double *final_err, double *v_err, int *n_out_p,
+                            int *restart_out_p, const kl_precond_t *M, const double *params, int nparams,
+                            int mf) {
+    if (!c || !A || !b || !x || !final_err || !v_err || !n_out_p || !restart_out_p) return KL_ERR_INVALID;
+    if (m < 1 || m + 1 > kMaxCols) return c->fail(KL_ERR_INVALID, "restart length m out of range");
+    Prob P;
+    KL_TRY(prob_init(&P, c, A, M, params, nparams, nx, ny));
+    const bool prec = P.pc.kind != KL_PC_NONE;
+    const bool fused = c->opt_fuse && P.builtin_op();
+    const size_t n = P.n;
+    const size_t ldv = (n + 31) & ~size_t(31);
+    const int ldh = m + 1;
+    const int vec = (n % 2 == 0) ? 2 : 1;
+    c->stats = kl_stats_t{};
+    cudaEvent_t evA, evB;
+    KL_CUDA(c, cudaEventCreate(&evA));
+    KL_CUDA(c, cudaEventCreate(&evB));
+    KL_CUDA(c, cudaEventRecord(evA, c->stream));
+
+    const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
+    size_t need = ws_need(ldv * (size_t)(m + 1)) + 6 * ws_need(n) + ws_need((size_t)ldh * m) +
+                  8 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
+    KL_TRY(ws_reserve(c, need));
+    ws_reset(c);
+    double *V = ws_take<double>(c, ldv * (size_t)(m + 1));
+    double *w = ws_take<double>(c, n), *z = ws_take<double>(c, n), *aux = ws_take<double>(c, n);
+    double *aux2 = ws_take<double>(c, n);
+    double *db = dev ? const_cast<double *>(b) : ws_take<double>(c, n);
+    double *dx = dev ? x : ws_take<double>(c, n);
+    GmresDev G;
+    G.H = ws_take<double>(c, (size_t)ldh * m);
+    G.g = ws_take<double>(c, m + 2);
+    G.cs = ws_take<double>(c, m + 2);
+    G.sn = ws_take<double>(c, m + 2);
+    G.y = ws_take<double>(c, m + 2);
+    G.fe = ws_take<double>(c, m + 2);
+    G.hvec = ws_take<double>(c, m + 2);
+    double *d_gram = ws_take<double>(c, (size_t)(m + 2) * (m + 2));
+    G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
+    G.m = m; G.ldh = ldh; G.mf = mf;
+
+    if (!dev) KL_TRY(stage_in(c, db, b, n));
+    KL_CUDA(c, cudaMemsetAsync(dx, 0, n * sizeof(double), c->stream));          // x = 0 (:304)
+    KL_CUDA(c, cudaMemsetAsync(G.fe, 0, (m + 2) * sizeof(double), c->stream));  // final_err = 0
+    KL_CUDA(c, cudaMemsetAsync(c->d_I, 0, sizeof(int) * I_COUNT, c->stream));
+    {
+        double S0[32] = {0};
+        S0[S_TOL] = tol;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_S, S0, sizeof S0, cudaMemcpyHostToDevice, c->stream));
+        int m1 = -1;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_I + I_CONV_AT, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    {   // beta0 = norm2(b) (:307)
+        PDot2 d;
+        set_gate(d, c, false);
+        d.a = db; d.b = db; d.c = nullptr; d.d = nullptr;
+        KL_TRY(launch_pointwise(c, d, n, PostStoreRed{c->d_S, S_BETA0, 1}));
+    }
+    KL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+
+    const int max_restarts = c->opt_max_restarts;
+    int status = KL_NOT_CONVERGED, n_out = 0, restart_out = max_restarts, cycles = 0;
+    double bytes = 0.0;
+    for (int st = 1; st <= max_restarts; ++st) {
+        ++cycles;
+        // g = 0 ; H = 0 (:312).  (V = 0 is not needed: every column is written before it is read.)
+        KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.cs, 0, sizeof(double) * (m + 2), c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.sn, 0, sizeof(double) * (m + 2), c->stream));
+        // w = M^-1 (b - A x) ; beta = ||w|| ; g(1) = beta (:314-324)
+        KL_TRY(op_resid(&P, dx, db, z, false));
+        if (prec) {
+            KL_TRY(pc_apply(&P, z, w, aux, aux2, 1, false, PostBeta{G}));
+        } else {
+            PDot2 d;
+            set_gate(d, c, false);
+            d.a = z; d.b = z; d.c = nullptr; d.d = nullptr;
+            KL_TRY(launch_pointwise(c, d, n, PostBeta{G}));
+            std::swap(w, z);
+        }
+        bytes += (24.0 + (prec ? 16.0 : 8.0)) * n;
+        int norm_idx = S_NORM;  // norm of the vector in `w` that becomes V_j
+        for (int j = 0; j < m; ++j) {
+            double *Vj = V + (size_t)j * ldv;
+            // V_j = w / norm ; z = A V_j   (:325-329 / :384 of the previous step ; :336).
+            // omp: V_j is also written when the previous step converged (:384 precedes :385).
+            if (fused) {
+                Halo H;
+                const double *vecs[1] = {w};
+                KL_TRY(halo_exchange(&P, vecs, 1, &H));
+                FScaleApply f;
+                set_io(f, &P, vecs, H);
+                set_gate(f, c, true, j - 1, mf ? 0 : 1);
+                f.v_out = Vj; f.z = z; f.S = c->d_S; f.s_idx = norm_idx;
+                KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, NoPost{}));
+            } else {
+                PScale s;
+                set_gate(s, c, true, j - 1, mf ? 0 : 1);
+                s.in = w; s.out = Vj; s.S = c->d_S; s.s_idx = norm_idx;
+                KL_TRY(launch_pointwise(c, s, n, NoPost{}));
+                KL_TRY(op_apply(&P, Vj, z, true));
+            }
+            // w = M^-1 z (:337)
+            if (prec) KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
+            else std::swap(w, z);
+            double *wj = w;
+            const int ncols = j + 1;
+            if (c->opt_ortho == KL_ORTHO_MGS2) {
+                // reference order: for k=1,2: for i=1..j: h = w.V_i ; H(i,j) += h ; w -= h V_i
+                const int total = 2 * ncols;
+                for (int t = 0; t <= total; ++t) {
+                    PMgsStep s;
+                    set_gate(s, c, true);
+                    s.w = wj; s.S = c->d_S;
+                    s.vprev = (t > 0) ? V + (size_t)((t - 1) % ncols) * ldv : nullptr;
+                    s.vcur = (t < total) ? V + (size_t)(t % ncols) * ldv : nullptr;
+                    s.want_norm = (t == total);
+                    if (t < total) {
+                        KL_TRY(launch_pointwise(c, s, n, PostMgs{G, j, t % ncols}));
+                    } else {
+                        // last axpy fused with ||w||^2 ; Givens after it
+                        KL_TRY(launch_pointwise(c, s, n, NoPost{}));
+                        k_givens<<<1, 32, sizeof(double) * 3 * (m + 2), c->stream>>>(G, j);
+                        c->stats.kernel_launches++;
+                    }
+                }
+                bytes += (32.0 * total + 24.0) * n;
+            } else {
+                KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 1, true));
+                KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, false, G, j, false, true));
+                KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 2, true));
+                KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, true, G, j, true, true));
+                bytes += (32.0 * ncols + 48.0) * n;
+            }
+            bytes += (24.0 + (prec ? 16.0 : 0.0)) * n;
+            norm_idx = S_HVAL;
+        }
+        // V_{m+1} = w / h_val (:384).  omp: also on the converged step ; mf: not (:172-176)
+        {
+            PScale s;
+            set_gate(s, c, true, m - 1, mf ? 0 : 1);
+            s.in = w; s.out = V + (size_t)m * ldv; s.S = c->d_S; s.s_idx = S_HVAL;
+            KL_TRY(launch_pointwise(c, s, n, NoPost{}));
+        }
+        k_backsolve<<<1, 32, sizeof(double) * 2 * m, c->stream>>>(G);                 // :394-398
+        if (vec == 2) k_xpvy<2><<<upd_grid(n / 2), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
+        else k_xpvy<1><<<upd_grid(n), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
+        c->stats.kernel_launches += 2;
+        KL_TRY(read_back(c));
+        n_out = c->h_pinned_i[I_NOUT];
+        bytes += (8.0 * n_out + 16.0) * n;
+        const double h_val = c->h_pinned[S_HVAL], fe = c->h_pinned[S_RES];
+        if (c->h_pinned_i[I_BREAKDOWN]) { status = KL_BREAKDOWN; restart_out = st; break; }
+        if (h_val < tol || fe < tol) {                                               // :409-412
+            restart_out = st;
+            status = KL_OK;
+            break;
+        }
+    }
+    KL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    // mf variant: the converged step leaves V(:,n_out+1) = 0 (exit precedes :176; V = 0 at :128)
+    if (mf && c->h_pinned_i[I_CONV_AT] >= 0)
+        KL_CUDA(c, cudaMemsetAsync(V + (size_t)(c->h_pinned_i[I_CONV_AT] + 1) * ldv, 0, n * sizeof(double), c->stream));
+    KL_TRY(stage_out(c, x, dx, n));
+    KL_CUDA(c, cudaMemcpyAsync(final_err, G.fe, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    KL_TRY(fetch_history(c));
+    for (int i = 0; i <= m; ++i) v_err[i] = 0.0;
+    c->stats.orth_frobenius = NAN;
+    if (c->opt_verr && n_out >= 1) {
+        // gmres_mgsr.f90:414-420 on the last cycle's basis, columns 0..n_out
+        const int k = n_out + 1;
+        std::vector<double> gr;
+        KL_TRY(gram_lower(c, V, ldv, n, k, d_gram, gr));
+        double fro = 0.0;
+        for (int col = 0; col < k; ++col)
+            for (int i = 0; i <= col; ++i) {
+                double d = gr[(size_t)col * k + i] - (i == col ? 1.0 : 0.0);
+                fro += (i == col ? 1.0 : 2.0) * d * d;
+            }
+        c->stats.orth_frobenius = sqrt(fro);
+        for (int j = 0; j < n_out; ++j) {
+            for (int i = 0; i <= j; ++i) {
+                double d = gr[(size_t)(j + 1) * k + i];
+                v_err[j + 1] = v_err[j + 1] + 2.0 * (d * d);
+            }
+            double dd = gr[(size_t)(j + 1) * k + (j + 1)] - 1.0;
+            v_err[j + 1] = v_err[j + 1] + dd * dd;
+            v_err[j + 1] = sqrt(v_err[j] * v_err[j] + v_err[j + 1]);
+        }
+    }
+    KL_CUDA(c, cudaEventRecord(evB, c->stream));
+    KL_CUDA(c, cudaStreamSynchronize(c->stream));
+    KL_CUDA(c, cudaGetLastError());
+    float ms = 0, ms_tot = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    cudaEventElapsedTime(&ms_tot, evA, evB);
+    cudaEventDestroy(evA);
+    cudaEventDestroy(evB);
+    c->stats.iterations = c->h_pinned_i[I_ITER];
+    c->stats.cycles = cycles;
+    c->stats.solve_ms = ms;
+    c->stats.total_ms = ms_tot;
+    c->stats.algorithmic_bytes = bytes;
+    *n_out_p = n_out;
+    *restart_out_p = restart_out;
+    return status;
+}
+
+}  // namespace kl
+
+using namespace kl;
+
+extern "C" {
+
+int kl_gmres_mgsr_omp(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+                      int m, double tol, double *final_err, double *v_err, int *n_out, int *restart_out,
+                      const kl_precond_t *M, const double *params, int nparams) {
+    return gmres_mgsr_solve(h, A, b, x, nx, ny, m, tol, final_err, v_err, n_out, restart_out, M, params,
+                            nparams, 0);
+}
+int kl_gmres_mgsr_mf(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+                     int m, double tol, double *final_err, double *v_err, int *n_out, int *restart_out,
+                     const kl_precond_t *M, const double *params, int nparams) {
+    return gmres_mgsr_solve(h, A, b, x, nx, ny, m, tol, final_err, v_err, n_out, restart_out, M, params,
+                            nparams, 1);
+}
+
+}  // extern "C"

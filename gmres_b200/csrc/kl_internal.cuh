@@ -1,0 +1,504 @@
+// kl_internal.cuh -- shared internals of libkrylov_b200 (sm_100a only).
+//
+// Design notes:
+//  * every kernel is FP64 and HBM-bound; no tensor cores on this path.
+//  * compiled with -fmad=false: every fused multiply-add is written as an
+//    explicit fma() so that point-wise results are bit-identical to the CPU
+//    oracle's (which is compiled with -ffp-contract=off and the same fma()s).
+//  * reductions are deterministic: per-block partial sums in a fixed order,
+//    summed by the last block to finish (threadfence + counter) in a fixed
+//    order.  The same launch configuration gives the same bits every run.
+//  * solver scalars (alpha, beta, Givens data, convergence flag, iteration
+//    counters, residual history) live in device memory; "post" functors run in
+//    the last block of the reducing kernel (single GPU) or in a 1-thread kernel
+//    after the NCCL all-reduce (multi GPU).  The host never sits between two
+//    kernels of an iteration.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/krylov_b200.h"
+
+namespace kl {
+
+// ------------------------------------------------------------------------
+// limits
+// ------------------------------------------------------------------------
+constexpr int kMaxRed = 8;          // reductions per point-wise / stencil kernel
+constexpr int kMaxBlocks = 4096;    // upper bound on reducing-kernel grid size
+constexpr int kMaxCols = 512;       // max restart length m+1 supported by the tall-skinny kernels
+constexpr int kNumSM = 148;
+
+// device scalar block layout (doubles)
+enum SIdx {
+    S_ALPHA = 0, S_BETA, S_OMEGA, S_RR, S_PAP, S_RES, S_TOL, S_BETA0, S_HVAL, S_NORM, S_TMP0,
+    S_TMP1, S_TMP2, S_TMP3, S_CD, S_CALPHA, S_RHO, S_RHOPREV, S_C1, S_C2, S_THETA, S_SCALE,
+    S_RED = 32,            // kMaxRed all-reduced sums land here (S_RED .. S_RED+7)
+    S_LAN = 64,            // lanczos alphas/betas etc.
+    S_COUNT = 1024
+};
+// device int block layout
+enum IIdx {
+    I_CONV_AT = 0,   // -1: running ; >=0: step/iteration index at which convergence was detected
+    I_ITER,          // iterations completed (CG/BiCGSTAB) / total inner iterations (GMRES)
+    I_NOUT,          // GMRES n_out of the current cycle
+    I_HIST,          // number of history entries written
+    I_BREAKDOWN,
+    I_STEP,
+    I_COUNT = 64
+};
+
+struct RedCtl {
+    double *partials;        // [grid * ld]
+    unsigned int *counter;   // zero between kernels
+    double *red;             // local sums destination
+};
+
+// ------------------------------------------------------------------------
+// host context
+// ------------------------------------------------------------------------
+}  // namespace kl
+struct kl_context_s;
+namespace kl {
+using Ctx = ::kl_context_s;
+int comm_allreduce(Ctx *c, double *d_buf, int count);
+int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *const *send_hi_rows,
+                       double *const *recv_lo, double *const *recv_hi, int nvec, int nx);
+
+}  // namespace kl
+
+struct kl_context_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int pointer_mode = KL_POINTER_HOST;
+    std::string err;
+    // options
+    int opt_ortho = KL_ORTHO_CGS2;
+    int opt_max_restarts = 1000;
+    int opt_verr = 1;
+    int opt_check_every = 32;
+    int opt_use_graph = 1;
+    int opt_hh_mode = KL_HH_SEQUENTIAL;
+    int opt_fuse = 1;
+    // comm
+    int rank = 0, nranks = 1;
+    void *nccl_comm = nullptr;
+    // device blocks
+    double *d_S = nullptr;
+    int *d_I = nullptr;
+    double *d_partials = nullptr;
+    unsigned int *d_counter = nullptr;
+    double *d_hist = nullptr;
+    int hist_cap = 0;
+    double *h_pinned = nullptr;   // pinned mirror for scalar read-back
+    int *h_pinned_i = nullptr;
+    // workspace arena (grown on demand, reused across calls)
+    char *ws = nullptr;
+    size_t ws_bytes = 0, ws_used = 0;
+    // halo buffers (multi GPU): up to 4 vectors x 2 directions
+    double *d_halo = nullptr;
+    size_t halo_doubles = 0;
+    // stats
+    kl_stats_t stats{};
+    std::vector<double> history;
+    int history_len = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s%s%s", what, e != cudaSuccess ? ": " : "",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "");
+        err = buf;
+        return code;
+    }
+};
+
+namespace kl {
+
+#define KL_CUDA(c, call)                                                     \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return (c)->fail(KL_ERR_CUDA, #call, e__);   \
+    } while (0)
+#define KL_TRY(call)                 \
+    do {                             \
+        int r__ = (call);            \
+        if (r__ < 0) return r__;     \
+    } while (0)
+
+// workspace arena
+int ws_reserve(Ctx *c, size_t bytes);
+inline void ws_reset(Ctx *c) { c->ws_used = 0; }
+template <class T>
+inline T *ws_take(Ctx *c, size_t count) {
+    size_t off = (c->ws_used + 255) & ~size_t(255);
+    c->ws_used = off + count * sizeof(T);
+    return reinterpret_cast<T *>(c->ws + off);
+}
+inline size_t ws_need(size_t count, size_t elt = 8) { return ((count * elt) + 255 + 256) & ~size_t(255); }
+
+// ------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming loads / stores: data touched once per kernel -> do not pollute L1
+__device__ __forceinline__ double2 ldg2(const double *p) {
+    return __ldg(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ void stg2(double *p, double a, double b) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+}
+
+// Block-level reduction of K values, deterministic; result valid in thread 0.
+template <int K, int NT>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *smem /* K * NT/32 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) smem[k * NW + wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int w = 0; w < NW; ++w) s += smem[k * NW + w];
+            v[k] = s;
+        }
+    }
+}
+
+// Grid-level deterministic reduction.  Every block calls this with its K block
+// sums valid in thread 0.  Returns true in ALL threads of the last block to
+// arrive, after red[0..K) holds the grid sums (summed over blocks in index
+// order by warp 0).  `nblocks` is the linear grid size, `bid` the linear id.
+template <int K>
+__device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc, unsigned nblocks,
+                                         unsigned bid, int *s_flag) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rc.partials[(size_t)k * kMaxBlocks + bid] = v[k];
+        __threadfence();
+        unsigned prev = atomicAdd(rc.counter, 1u);
+        *s_flag = (prev == nblocks - 1);
+    }
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const volatile double *p = rc.partials + (size_t)k * kMaxBlocks;
+            double s = 0.0;
+            for (unsigned b = lane; b < nblocks; b += 32) s += p[b];
+            s = warp_sum(s);
+            if (lane == 0) rc.red[k] = s;
+        }
+        if (lane == 0) {
+            *rc.counter = 0u;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// ------------------------------------------------------------------------
+// 5-point operator arithmetic.  OPK selects the reference's rounding order.
+//   l = x(i-1), r = x(i+1), dn = x(idx+n) (next line), up = x(idx-n).
+//   missing neighbours are passed as 0.0 (adding/subtracting 0.0 is exact, so
+//   this reproduces every edge/corner formula of poisson.f90:47-76).
+// ------------------------------------------------------------------------
+struct OpCoef {
+    double ex, ey, cc;
+};
+template <int OPK>
+__device__ __forceinline__ double apply5(double c, double l, double r, double dn, double up,
+                                         const OpCoef &k) {
+    if (OPK == KL_OP_POISSON5) {
+        // poisson.f90:42  4*x - 1*(((x(idx-1)+x(idx+1))+x(idx+n))+x(idx-n))
+        return 4.0 * c - (((l + r) + dn) + up);
+    } else if (OPK == KL_OP_POISSON5_BRANCHY) {
+        // poisson.f90:88-92  ((((4x - x(idx-1)) - x(idx+1)) - x(idx-n)) - x(idx+n))
+        return (((4.0 * c - l) - r) - up) - dn;
+    } else {
+        double sx = l + r, sy = dn + up;
+        double t = fma(k.ex, sx, k.ey * sy);
+        return fma(k.cc, c, -t);
+    }
+}
+
+// ------------------------------------------------------------------------
+// Marching stencil kernel framework.
+//
+// A functor F describes a point-wise "input field" u (evaluated on the fly from
+// NIN arrays, e.g. u = r/d or u = z + beta*p), the kernel applies the 5-point
+// operator to u and hands (u, A u) to F::store, which writes outputs and
+// accumulates up to NRED reductions.  Each thread owns VEC adjacent columns and
+// marches down `rows` lines keeping three lines of u in registers, so every
+// input element is loaded from L2/HBM once per block (plus 2 halo lines per
+// `rows`).  Left/right neighbours come from warp shuffles; warp-edge lanes
+// evaluate one extra scalar.
+//
+// Multi-GPU: lo/hi are the neighbour ranks' boundary lines of the NIN input
+// arrays (nullptr at the global boundary => zero Dirichlet).
+// ------------------------------------------------------------------------
+struct Geo {
+    int nx, ny, rows;
+};
+
+template <int NIN_, int NRED_>
+struct StencilBase {
+    static constexpr int NIN = NIN_;
+    static constexpr int NRED = NRED_;
+    const double *in[NIN_];
+    const double *lo[NIN_];
+    const double *hi[NIN_];
+    const int *flags;
+    int step;         // gating: run iff flags[I_CONV_AT] < 0 (or == step when run_on_conv)
+    int run_on_conv;
+    OpCoef coef;
+    __device__ __forceinline__ bool skip() const {
+        if (!flags) return false;
+        int ca = flags[I_CONV_AT];
+        return !(ca < 0 || (run_on_conv && ca == step));
+    }
+};
+
+constexpr int kStencilThreads = 128;
+
+template <class F, int OPK, int VEC, class Post>
+__global__ void __launch_bounds__(kStencilThreads)
+k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post) {
+    if (f_in.skip()) return;
+    F f = f_in;
+    f.init();
+    constexpr int NIN = F::NIN;
+    constexpr int NRED = F::NRED;
+    const int lane = threadIdx.x & 31;
+    const int i0 = (blockIdx.x * kStencilThreads + threadIdx.x) * VEC;
+    const bool act = i0 < g.nx;
+    const int j0 = blockIdx.y * g.rows;
+    const int j1 = min(j0 + g.rows, g.ny);
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (NRED > 0 ? NRED : 1); ++k) acc[k] = 0.0;
+
+    auto rowptrs = [&](int j, const double *(&rp)[NIN]) -> bool {
+        if (j < 0) {
+            if (f.lo[0] == nullptr) return false;
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) rp[a] = f.lo[a];
+        } else if (j >= g.ny) {
+            if (f.hi[0] == nullptr) return false;
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) rp[a] = f.hi[a];
+        } else {
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) rp[a] = f.in[a] + (size_t)j * g.nx;
+        }
+        return true;
+    };
+    auto load_row = [&](int j, double (&u)[VEC]) {
+        const double *rp[NIN];
+        if (act && rowptrs(j, rp)) {
+            f.template eval<VEC>(rp, i0, u);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) u[v] = 0.0;
+        }
+    };
+
+    double up[VEC], cu[VEC], dn[VEC];
+    load_row(j0 - 1, up);
+    load_row(j0, cu);
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        load_row(j + 1, dn);
+        double l = __shfl_up_sync(0xffffffffu, cu[VEC - 1], 1);
+        double r = __shfl_down_sync(0xffffffffu, cu[0], 1);
+        if (lane == 0 || lane == 31) {
+            const double *rp[NIN];
+            rowptrs(j, rp);
+            if (lane == 0) {
+                double t[1] = {0.0};
+                if (act && i0 > 0) f.template eval<1>(rp, i0 - 1, t);
+                l = t[0];
+            } else {
+                double t[1] = {0.0};
+                if (act && i0 + VEC < g.nx) f.template eval<1>(rp, i0 + VEC, t);
+                r = t[0];
+            }
+        }
+        if (act) {
+            double au[VEC];
+            if (VEC == 1) {
+                au[0] = apply5<OPK>(cu[0], l, r, dn[0], up[0], f.coef);
+            } else {
+                au[0] = apply5<OPK>(cu[0], l, cu[VEC - 1], dn[0], up[0], f.coef);
+                au[VEC - 1] = apply5<OPK>(cu[VEC - 1], cu[0], r, dn[VEC - 1], up[VEC - 1], f.coef);
+            }
+            f.template store<VEC>((size_t)j * g.nx + i0, cu, au, acc);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            up[v] = cu[v];
+            cu[v] = dn[v];
+        }
+    }
+    if (NRED > 0) {
+        __shared__ double sm[(NRED > 0 ? NRED : 1) * (kStencilThreads / 32)];
+        __shared__ int s_flag;
+        block_sum<(NRED > 0 ? NRED : 1), kStencilThreads>(acc, sm);
+        const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        if (grid_sum<(NRED > 0 ? NRED : 1)>(acc, rc, nb, bid, &s_flag)) {
+            if (fuse_post && threadIdx.x == 0) post.run();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------
+// Point-wise kernel framework: grid-stride over VEC-wide chunks, UNR chunks
+// per thread per trip.  F::elem<VEC>(idx, acc) loads, computes and stores.
+// ------------------------------------------------------------------------
+constexpr int kPwThreads = 256;
+
+template <class F, int VEC, class Post>
+__global__ void __launch_bounds__(kPwThreads)
+k_pointwise(const F f_in, const size_t n, const RedCtl rc, const Post post, const int fuse_post) {
+    if (f_in.skip()) return;
+    F f = f_in;
+    f.init();
+    constexpr int NRED = F::NRED;
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (NRED > 0 ? NRED : 1); ++k) acc[k] = 0.0;
+    const size_t nchunk = n / VEC;
+    const size_t stride = (size_t)gridDim.x * kPwThreads;
+#pragma unroll 4
+    for (size_t c = (size_t)blockIdx.x * kPwThreads + threadIdx.x; c < nchunk; c += stride)
+        f.template elem<VEC>(c * VEC, acc);
+    if (NRED > 0) {
+        __shared__ double sm[(NRED > 0 ? NRED : 1) * (kPwThreads / 32)];
+        __shared__ int s_flag;
+        block_sum<(NRED > 0 ? NRED : 1), kPwThreads>(acc, sm);
+        if (grid_sum<(NRED > 0 ? NRED : 1)>(acc, rc, gridDim.x, blockIdx.x, &s_flag)) {
+            if (fuse_post && threadIdx.x == 0) post.run();
+        }
+    }
+}
+
+template <int NRED_>
+struct PwBase {
+    static constexpr int NRED = NRED_;
+    const int *flags;
+    int step;
+    int run_on_conv;
+    __device__ __forceinline__ bool skip() const {
+        if (!flags) return false;
+        int ca = flags[I_CONV_AT];
+        return !(ca < 0 || (run_on_conv && ca == step));
+    }
+};
+
+struct NoPost {
+    __device__ __forceinline__ void run() const {}
+};
+
+// post functor launched on its own (multi-GPU: after the all-reduce)
+template <class Post>
+__global__ void k_post(const Post post) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) post.run();
+}
+
+// ------------------------------------------------------------------------
+// launch helpers (host)
+// ------------------------------------------------------------------------
+inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED}; }
+
+inline int stencil_rows(int nx, int ny, int vec) {
+    // aim for >= ~8 blocks per SM, between 8 and 64 lines per block
+    long gx = (nx + kStencilThreads * vec - 1) / (kStencilThreads * vec);
+    long want = (long)kNumSM * 8;
+    long rows = ((long)ny * gx + want - 1) / want;
+    if (rows < 8) rows = 8;
+    if (rows > 64) rows = 64;
+    if (rows > ny) rows = ny;
+    return (int)rows;
+}
+
+// after a reducing kernel: single GPU => post already ran fused; multi GPU =>
+// all-reduce the local sums and run the post functor in its own kernel.
+template <class Post>
+inline int finish_reduction(Ctx *c, int nred, const Post &post) {
+    if (c->nranks > 1) {
+        KL_TRY(comm_allreduce(c, c->d_S + S_RED, nred));
+        k_post<Post><<<1, 32, 0, c->stream>>>(post);
+        c->stats.kernel_launches++;
+    }
+    return KL_OK;
+}
+
+template <class F, class Post>
+inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, const Post &post) {
+    const int vec = (nx % 2 == 0) ? 2 : 1;
+    Geo g{nx, ny, stencil_rows(nx, ny, vec)};
+    dim3 grid((nx + kStencilThreads * vec - 1) / (kStencilThreads * vec), (ny + g.rows - 1) / g.rows);
+    if ((long)grid.x * grid.y > kMaxBlocks) {
+        g.rows = (int)(((long)ny * grid.x + kMaxBlocks - 1) / kMaxBlocks);
+        grid.y = (ny + g.rows - 1) / g.rows;
+    }
+    f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
+    RedCtl rc = redctl(c);
+    const int fuse = c->nranks == 1;
+#define KL_ST_LAUNCH(OPK)                                                                         \
+    if (vec == 2)                                                                                 \
+        k_stencil<F, OPK, 2, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse); \
+    else                                                                                          \
+        k_stencil<F, OPK, 1, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);
+    switch (op->kind) {
+        case KL_OP_POISSON5: KL_ST_LAUNCH(KL_OP_POISSON5) break;
+        case KL_OP_POISSON5_BRANCHY: KL_ST_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
+        case KL_OP_ANISO5: KL_ST_LAUNCH(KL_OP_ANISO5) break;
+        default: return c->fail(KL_ERR_INVALID, "launch_stencil: not a built-in operator");
+    }
+#undef KL_ST_LAUNCH
+    c->stats.kernel_launches++;
+    if (F::NRED > 0) return finish_reduction(c, F::NRED, post);
+    return KL_OK;
+}
+
+inline int pw_grid(size_t nchunk) {
+    size_t b = (nchunk + kPwThreads * 4 - 1) / (kPwThreads * 4);
+    size_t cap = (size_t)kNumSM * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <class F, class Post>
+inline int launch_pointwise(Ctx *c, F f, size_t n, const Post &post) {
+    RedCtl rc = redctl(c);
+    const int fuse = c->nranks == 1;
+    if (n % 2 == 0)
+        k_pointwise<F, 2, Post><<<pw_grid(n / 2), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
+    else
+        k_pointwise<F, 1, Post><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
+    c->stats.kernel_launches++;
+    if (F::NRED > 0) return finish_reduction(c, F::NRED, post);
+    return KL_OK;
+}
+
+}  // namespace kl
