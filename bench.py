@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- Krylov iterations/s on synthetic Poisson grids, B200 vs the CPU path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload cg16384|gmres4096|...]
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is ONE Krylov iteration.  The primary workload is BASELINE.json configs[3]:
+CG on the 16384 x 16384 Poisson grid (268 M unknowns), strong-scaled over N GPUs by
+row slabs (halo send/recv + scalar all-reduces).  At N=1 the JSON line also carries
+`extra` results for configs[2] (Chebyshev-preconditioned GMRES-MGSR(95), 4096^2),
+configs[1] (Householder GMRES(95), 1024^2) and configs[4] (BiCGSTAB, 8192^2/GPU).
+
+Inputs are synthetic and deterministic (x_true = 1, b = A*1; no RNG), resident in HBM
+before the timed region; vectors (2.1 GB each) are far larger than the 126 MB L2, so no
+L2 flush is needed between iterations.  Timing: CUDA events on the launching stream
+around exactly K iterations (tol = 0 so nothing converges early), barrier + device sync
+on both sides, MAX over ranks.
+
+`--impl reference`: the reference is Fortran and no Fortran compiler exists on the
+build or GPU box, so this arm times the C/OpenMP restatement of the reference's
+`cg_omp` (oracle/, same loop/barrier structure) on all host cores, on a bounded
+number of iterations of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_REF = (8.2, 0.2)  # tests/test_poisson_mf.f90:38
+
+WORKLOADS = {
+    # name: (solver, nx, ny_per_gpu_or_global, scaling, precond, m, bytes_per_iter_per_unknown)
+    "cg16384": dict(solver="cg_omp", nx=16384, ny=16384, scaling="strong", pc=None, m=0),
+    "pcg16384": dict(solver="pcg_omp", nx=16384, ny=16384, scaling="strong", pc="cbpr2", m=0),
+    "gmres4096": dict(solver="gmres_mgsr_omp", nx=4096, ny=4096, scaling="strong", pc="cbpr2", m=95),
+    "hh1024": dict(solver="gmres_hh_omp", nx=1024, ny=1024, scaling="strong", pc=None, m=95),
+    "bicgstab8192": dict(solver="pbicgstab_omp", nx=8192, ny=8192, scaling="weak", pc="cbpr2", m=0,
+                         aniso=(1.0, 0.01)),
+    "gmres300": dict(solver="gmres_mgsr_omp", nx=300, ny=300, scaling="strong", pc="cbpr2", m=95),
+    "cg4096": dict(solver="cg_omp", nx=4096, ny=4096, scaling="strong", pc=None, m=0),
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw)}
+
+
+def make_ops(kl, w):
+    A = kl.aniso(*w["aniso"]) if w.get("aniso") else kl.stvec
+    M = kl.cbpr2 if w["pc"] == "cbpr2" else None
+    return A, M
+
+
+def run_gpu_solver(kl, h, w, b, nx, ny, iters, profile=False):
+    """Run exactly `iters` iterations (tol = 0 => never converges).  Returns result."""
+    A, M = make_ops(kl, w)
+    h.set_option(3, 0)        # KL_OPT_VERR off: the epilogue is not part of an iteration
+    h.set_option(8, 1 if profile else 0)
+    s = w["solver"]
+    if s in ("cg_omp", "pcg_omp", "pbicgstab_omp"):
+        h.set_option(4, max(iters, 1))   # one host poll at the end
+        if s == "cg_omp":
+            return h.cg_omp(A, b, 0.0, iters, nx=nx, ny=ny)
+        if s == "pcg_omp":
+            return h.pcg_omp(A, b, 0.0, iters, M, P_REF, nx=nx, ny=ny)
+        return h.pbicgstab_omp(A, b, 0.0, iters, M, P_REF, nx=nx, ny=ny)
+    m = w["m"]
+    cycles = max(1, iters // m)
+    h.set_option(2, cycles)   # KL_OPT_MAX_RESTARTS
+    if s == "gmres_mgsr_omp":
+        return h.gmres_mgsr_omp(A, b, m, 0.0, M, P_REF, nx=nx, ny=ny)
+    if s == "gmres_hh_omp":
+        return h.gmres_hh_omp(A, b, m, 0.0, nx=nx, ny=ny)
+    raise ValueError(s)
+
+
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    import gmres_b200 as kl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    h = kl.Handle(local)
+    if world > 1:
+        ids = [h.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        h.comm_init(rank, world, ids[0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(name, steps, warmup, with_e2e, with_profile):
+        w = WORKLOADS[name]
+        nx = w["nx"]
+        ny = w["ny"] * (world if w["scaling"] == "weak" else 1)   # global lines
+        j0, nyl = h.partition(ny)
+        n_loc = nx * nyl
+        A, M = make_ops(kl, w)
+        # b = A*1 built by the operator itself on this rank's slab (+ global boundary rows)
+        ones = torch.ones(n_loc, dtype=torch.float64, device="cuda")
+        b = h.apply(A, ones, nx, ny)
+        del ones
+        m = w["m"] or 1
+        steps_eff = max(m, (steps // m) * m) if w["m"] else steps
+        warm_eff = max(m, (warmup // m) * m) if w["m"] else max(warmup, 3)
+        run_gpu_solver(kl, h, w, b, nx, ny, warm_eff)                    # warm-up (untimed)
+        barrier()
+        smp = ClockSampler(local)
+        if rank == 0:
+            smp.start()
+        r = run_gpu_solver(kl, h, w, b, nx, ny, steps_eff)               # timed: events inside the library
+        barrier()
+        clocks = smp.stop() if rank == 0 else None
+        ms = max_over_ranks(r.stats["solve_ms"])
+        its = r.stats["iterations"]
+        launches = r.stats["kernel_launches"]
+        out = dict(workload=name, iterations=its, ms=ms, ms_per_step=ms / max(its, 1),
+                   its_per_s=its / (ms * 1e-3), launches=int(launches), clocks=clocks,
+                   bytes_per_iter=r.stats["algorithmic_bytes"] / max(its, 1) * world,
+                   n_unknowns=nx * ny, nx=nx, ny=ny)
+        peak, which = load_peaks()
+        out["roofline_iter"] = dict(
+            bound="hbm", achieved=r.stats["algorithmic_bytes"] / (ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+            frac=r.stats["algorithmic_bytes"] / (ms * 1e-3) / 1e9 / peak, peak_source=which,
+            note="per-GPU algorithmic bytes of all executed kernels / CUDA-event time of the iteration loop")
+        if with_profile:
+            rp = run_gpu_solver(kl, h, w, b, nx, ny, steps_eff, profile=True)
+            barrier()
+            prof = h.profile()
+            tot = sum(p["ms"] for p in prof) or 1.0
+            for p in prof:
+                p["avg_us"] = 1e3 * p["ms"] / p["launches"]
+                p["gbs"] = p["algorithmic_bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+                p["frac_of_peak"] = p["gbs"] / peak
+                p["share"] = p["ms"] / tot
+            out["kernels"] = prof
+            dom = max(prof, key=lambda p: p["ms"]) if prof else None
+            if dom:
+                out["roofline"] = dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s",
+                                       frac=dom["gbs"] / peak, traffic=None, kernel=dom["name"],
+                                       avg_launch_us=dom["avg_us"], peak_source=which)
+            h.set_option(8, 0)
+        if with_e2e:
+            # the reference-facing call with HOST buffers: H2D of b and D2H of x inside the timed region
+            bh = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+            bh.copy_(b)
+            del b
+            torch.cuda.empty_cache()
+            bn = bh.numpy()
+            barrier()
+            t0 = time.perf_counter()
+            r2 = run_gpu_solver(kl, h, w, bn, nx, ny, steps_eff)
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            tot_ms = max_over_ranks(r2.stats["total_ms"])
+            out["e2e"] = dict(value=r2.stats["iterations"] / (tot_ms * 1e-3), unit="iterations/s",
+                              h2d_bytes_per_step=r2.stats["h2d_bytes"] * world / max(r2.stats["iterations"], 1),
+                              d2h_bytes_per_step=r2.stats["d2h_bytes"] * world / max(r2.stats["iterations"], 1),
+                              total_ms=tot_ms, wall_ms=wall * 1e3,
+                              note="one solver call of K iterations through the C ABI with host buffers "
+                                   "(b uploaded, x downloaded once per call; device event time incl. copies)")
+        return out
+
+    primary = measure(args.workload, args.steps, args.warmup, True, True)
+    extras = {}
+    if world == 1 and args.extras:
+        for name, st in (("gmres4096", 95), ("pcg16384", args.steps), ("bicgstab8192", args.steps),
+                         ("hh1024", 95), ("gmres300", 475)):
+            if name == args.workload:
+                continue
+            try:
+                e = measure(name, st, st if WORKLOADS[name]["m"] else 3, False, True)
+                extras[name] = {k: e[k] for k in ("iterations", "ms_per_step", "its_per_s", "launches",
+                                                    "roofline_iter", "kernels") if k in e}
+            except Exception as ex:  # pragma: no cover
+                extras[name] = {"error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        cpu = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        w = WORKLOADS[args.workload]
+        line = {
+            "metric": "krylov_iterations_per_s", "value": primary["its_per_s"], "unit": "iterations/s",
+            "n_gpus": world, "steps": primary["iterations"], "warmup": args.warmup,
+            "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (x_true=1, b=A*1, no RNG)",
+            "config": {"workload": f"{w['solver']} Poisson 2D 5-point {primary['nx']}x{primary['ny']} "
+                                   f"({primary['n_unknowns']} unknowns), tol=0 (fixed K iterations)",
+                       "name": args.workload, "partition": f"row-slab x{world}",
+                       "l2": "inputs larger than L2 (no flush needed)", "bytes_per_iteration": primary["bytes_per_iter"]},
+            "clocks": primary["clocks"], "gpu_launches": primary["launches"],
+            "roofline": primary.get("roofline"), "roofline_iter": primary["roofline_iter"],
+            "kernels": primary.get("kernels"), "e2e": primary.get("e2e"),
+            "cpu_baseline": cpu, "extra": extras,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, budget_s=20.0, threads=None):
+    """Time the oracle (C/OpenMP restatement of the reference's *_omp routine) on the host."""
+    import numpy as np
+    from oracle import oracle as ko
+
+    w = WORKLOADS[workload]
+    cores = threads or os.cpu_count()
+    ko.set_threads(cores)
+    ns = w["nx"]
+    n = ns * ns
+    A = ko.stvec_fn()
+    M = ko.cbpr2_fn() if w["pc"] else None
+    b = np.zeros(n)
+    b.reshape(ns, ns)[0, :] += 1; b.reshape(ns, ns)[-1, :] += 1
+    b.reshape(ns, ns)[:, 0] += 1; b.reshape(ns, ns)[:, -1] += 1       # b = A*1 (values 0/1/2)
+
+    def run(iters):
+        t0 = time.perf_counter()
+        if w["solver"] == "cg_omp":
+            ko.cg_omp(A, b, 0.0, iters, history_cap=1)
+        elif w["solver"] == "pcg_omp":
+            ko.pcg_omp(A, b, 0.0, iters, M, P_REF, history_cap=1)
+        elif w["solver"] == "pbicgstab_omp":
+            ko.pbicgstab_omp(A, b, 0.0, iters, M, P_REF, history_cap=1)
+        elif w["solver"] == "gmres_mgsr_omp":
+            ko.gmres_mgsr_omp(A, b, iters, 0.0, M, P_REF, max_restarts=1, skip_verr=True, history_cap=1)
+        else:
+            ko.gmres_hh(A, b, iters, 0.0, None, max_stages=1, skip_verr=True, history_cap=1)
+        return time.perf_counter() - t0
+
+    # calibrate: a short run (setup + i0 iterations), then a longer one; rate from the difference
+    i0 = 2
+    t_short = run(i0)
+    per_it = max(t_short / (i0 + 2), 1e-4)
+    i1 = int(min(max((budget_s * 0.6) / per_it, i0 + 3), 400))
+    if w["m"]:
+        i1 = min(i1, w["m"])
+    t_long = run(i1)
+    rate = (i1 - i0) / max(t_long - t_short, 1e-9)
+    return {"value": rate, "unit": "iterations/s", "cores": cores, "kind": "port",
+            "sample": f"{w['solver']} on {ns}x{ns}: ({i1}-{i0}) iterations, time difference of two runs "
+                      f"({t_long:.2f}s - {t_short:.2f}s) so that allocation/first-touch cancels; "
+                      f"oracle/krylov_oracle.c, gcc -O3 -fopenmp, OMP threads = {cores}"}
+
+
+def reference_arm(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cb = cpu_baseline(args.workload, budget_s=max(10.0, min(120.0, 2.0 * (args.steps + args.warmup))))
+    line = {
+        "impl": "reference", "metric": "krylov_iterations_per_s", "value": cb["value"], "unit": "iterations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (x_true=1, b=A*1, no RNG)",
+        "config": {"workload": f"{w['solver']} Poisson 2D 5-point {w['nx']}x{w['ny']}", "name": args.workload,
+                   "note": "reference is Fortran; no Fortran compiler on this box: C/OpenMP restatement "
+                           "(oracle/) of the same routine on all host cores"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cg16384", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", dest="extras", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ KL_OP_POISSON5, KL_OP_POISSON5_BRANCHY, KL_OP_ANISO5, KL_OP_USER = 0, 1, 2, 100
 KL_PC_NONE, KL_PC_CBPR2, KL_PC_CHEB, KL_PC_USER = 0, 1, 2, 100
 KL_POINTER_HOST, KL_POINTER_DEVICE = 0, 1
 (KL_OPT_ORTHO, KL_OPT_MAX_RESTARTS, KL_OPT_VERR, KL_OPT_CHECK_EVERY, KL_OPT_USE_GRAPH,
- KL_OPT_HH_MODE, KL_OPT_FUSE) = range(1, 8)
+ KL_OPT_HH_MODE, KL_OPT_FUSE, KL_OPT_PROFILE) = range(1, 9)
 ORTHO_MGS2, ORTHO_CGS2, ORTHO_CGS2_SELECTIVE = 0, 1, 2
 HH_SEQUENTIAL, HH_BLOCKED = 0, 1
 KL_UNIQUE_ID_BYTES = 128
@@ -118,6 +118,7 @@ def load_library():
     L.kl_cheb_params_from_ritz.argtypes = [C.c_double, C.c_double, _dp]
     L.kl_get_history.argtypes = [C.c_void_p, _dp, C.c_int, _ip]
     L.kl_get_stats.argtypes = [C.c_void_p, C.POINTER(kl_stats_t)]
+    L.kl_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong), _dp]
     L.kl_vec_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.kl_vec_free.argtypes = [C.c_void_p, C.c_void_p]
     L.kl_vec_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -276,6 +277,18 @@ class Handle:
         s = kl_stats_t()
         self._chk(self._L.kl_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def profile(self) -> list:
+        """Per-kernel-class CUDA-event timers of the last solve (KL_OPT_PROFILE = 1)."""
+        out = []
+        for i in range(8):
+            name, ms, ln, by = C.c_char_p(), C.c_double(), C.c_longlong(), C.c_double()
+            if self._L.kl_get_profile(self._h, i, C.byref(name), C.byref(ms), C.byref(ln), C.byref(by)) != 0:
+                break
+            if ln.value:
+                out.append(dict(name=name.value.decode() if name.value else f"class{i}", ms=ms.value,
+                                launches=ln.value, algorithmic_bytes=by.value))
+        return out
 
     def history(self) -> np.ndarray:
         n = C.c_int()

@@ -58,6 +58,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     const size_t n = P.n;
     const int maxit = *iter;
     c->stats = kl_stats_t{};
+    prof_reset(c);
     cudaEvent_t evA, evB;
     KL_CUDA(c, cudaEventCreate(&evA));
     KL_CUDA(c, cudaEventCreate(&evB));
@@ -109,6 +110,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
         for (int k = 0; k < batch; ++k) {
             // ---- K1
             if (fused) {
+                ProfScope ps(c, 0, "cg_dir_apply_dot (stencil: p=z+beta*p; ax=A p; ax.p)", 32.0 * n);
                 Halo H;
                 const double *vecs[2] = {z, pold};
                 KL_TRY(halo_exchange(&P, vecs, 2, &H));
@@ -130,6 +132,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
             }
             // ---- K2
             {
+                ProfScope ps(c, 1, "cg_update_xr_dot (pointwise: x+=alpha p; r-=alpha ax; r.r)", 48.0 * n);
                 PCgUpdate u;
                 set_gate(u, c, true);
                 u.x = dx; u.r = r; u.p = pnew; u.ax = ax; u.S = c->d_S;
@@ -137,9 +140,11 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
                 else KL_TRY(launch_pointwise(c, u, n, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}));
             }
             // ---- K3
-            if (prec)
+            if (prec) {
+                ProfScope ps(c, 2, "pcg_precond_dot (stencil: z=M^-1 r; r.z)", 16.0 * n);
                 KL_TRY(pc_apply(&P, r, z, aux, aux2, 2, true,
                                 PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 1}));
+            }
             double *t = pold; pold = pnew; pnew = t;
         }
         done += batch;
@@ -156,6 +161,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     KL_CUDA(c, cudaEventRecord(evB, c->stream));
     KL_CUDA(c, cudaStreamSynchronize(c->stream));
     KL_CUDA(c, cudaGetLastError());
+    prof_resolve(c);
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);

@@ -23,6 +23,36 @@ int ws_reserve(Ctx *c, size_t bytes) {
     return KL_OK;
 }
 
+void prof_reset(Ctx *c) {
+    for (auto &r : c->prof_recs) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
+    c->prof_recs.clear();
+    for (int i = 0; i < KL_PROFILE_CLASSES; ++i) {
+        c->prof_ms[i] = 0; c->prof_launches[i] = 0; c->prof_bytes[i] = 0; c->prof_name[i] = nullptr;
+    }
+}
+static cudaEvent_t prof_event(Ctx *c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(Ctx *c, int cls, const char *name, double bytes) {
+    Ctx::ProfRec r{cls, prof_event(c), prof_event(c)};
+    c->prof_name[cls] = name;
+    c->prof_bytes[cls] += bytes;
+    c->prof_launches[cls] += 1;
+    cudaEventRecord(r.a, c->stream);
+    c->prof_recs.push_back(r);
+}
+void prof_end(Ctx *c) { cudaEventRecord(c->prof_recs.back().b, c->stream); }
+void prof_resolve(Ctx *c) {
+    for (auto &r : c->prof_recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) c->prof_ms[r.cls] += ms;
+    }
+    cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------
 // NCCL, loaded at run time (dlopen) so that the library has no link-time
 // dependency on it: single-GPU users and CPU-only symbol checks never need it,
@@ -177,6 +207,8 @@ int kl_destroy(kl_handle_t h) {
     if (c->h_pinned_i) cudaFreeHost(c->h_pinned_i);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    prof_reset(c);
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return KL_OK;
@@ -233,6 +265,7 @@ int kl_set_option(kl_handle_t h, int key, int value) {
             h->opt_hh_mode = value;
             break;
         case KL_OPT_FUSE: h->opt_fuse = value != 0; break;
+        case KL_OPT_PROFILE: h->opt_profile = value != 0; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;
@@ -248,6 +281,7 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_USE_GRAPH: *value = h->opt_use_graph; break;
         case KL_OPT_HH_MODE: *value = h->opt_hh_mode; break;
         case KL_OPT_FUSE: *value = h->opt_fuse; break;
+        case KL_OPT_PROFILE: *value = h->opt_profile; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;
@@ -349,6 +383,16 @@ int kl_get_history(kl_handle_t h, double *out, int cap, int *len) {
 int kl_get_stats(kl_handle_t h, kl_stats_t *out) {
     if (!h || !out) return KL_ERR_INVALID;
     *out = h->stats;
+    return KL_OK;
+}
+
+int kl_get_profile(kl_handle_t h, int idx, const char **name, double *ms, long long *launches,
+                   double *algorithmic_bytes) {
+    if (!h || idx < 0 || idx >= KL_PROFILE_CLASSES) return KL_ERR_INVALID;
+    if (name) *name = h->prof_name[idx];
+    if (ms) *ms = h->prof_ms[idx];
+    if (launches) *launches = h->prof_launches[idx];
+    if (algorithmic_bytes) *algorithmic_bytes = h->prof_bytes[idx];
     return KL_OK;
 }
 

@@ -24,80 +24,14 @@
 
 #include <algorithm>
 
-#include "kl_ops.cuh"
+#include "kl_gmres.cuh"
 
 namespace kl {
-
-constexpr int kTsThreads = 256;
-constexpr int kTsWarps = kTsThreads / 32;
-constexpr int kTsCpw = 12;          // columns per warp per pass
-constexpr int kTsU = 4;             // row chunks per lane per trip
-constexpr int kTsMaxBlocks = 1024;  // partials leading dimension
-
-struct GmresDev {
-    double *H;      // (m+1) x m, ldh = m+1
-    double *g, *cs, *sn, *y, *fe, *hvec;
-    double *S;
-    int *I;
-    double *hist;
-    int hist_cap;
-    int m, ldh;
-    int mf;         // 1: gmres_mgsr_mf semantics (h_val < tol also stops; :172)
-};
-
-// ---- Givens update by ONE WARP (gmres_mgsr.f90:362-389) --------------------
-// sumsq = ||w||^2 after orthogonalisation.  Called by warp 0 of the last block
-// of the final update kernel (single GPU) or by k_givens (multi GPU).
-__device__ __forceinline__ void givens_update_warp(const GmresDev &G, int j, double sumsq, int lane,
-                                                   double *sm /* 3*(m+2) doubles */) {
-    double *sh = sm, *sc = sm + (G.m + 2), *ss = sm + 2 * (G.m + 2);
-    double *Hj = G.H + (size_t)j * G.ldh;
-    for (int i = lane; i <= j; i += 32) sh[i] = Hj[i];
-    for (int i = lane; i < j; i += 32) {
-        sc[i] = G.cs[i];
-        ss[i] = G.sn[i];
-    }
-    __syncwarp();
-    if (lane == 0) {
-        const double h_val = sqrt(sumsq);                 // :362 norm2(w)
-        double hi = sh[0];
-        for (int i = 0; i < j; ++i) {                     // :365-369
-            const double hn = sh[i + 1], c = sc[i], s = ss[i];
-            Hj[i] = fma(c, hi, s * hn);
-            hi = fma(-s, hi, c * hn);
-        }
-        // hi = H(j,j) after the previous rotations; H(j+1,j) = h_val (:363)
-        const double hjj = hi, hj1 = h_val;
-        double ds = hypot(hj1, hjj);                      // :370
-        double c = hjj / ds, s = hj1 / ds;                // :371-372
-        G.cs[j] = c;
-        G.sn[j] = s;
-        Hj[j] = fma(c, hjj, s * hj1);                     // :373
-        Hj[j + 1] = 0.0;                                  // :374
-        double tmp = G.g[j], gn = G.g[j + 1];             // :378-380
-        G.g[j] = fma(c, tmp, s * gn);
-        double gj1 = fma(-s, tmp, c * gn);
-        G.g[j + 1] = gj1;
-        double fe = fabs(gj1) / G.S[S_BETA0];             // :383
-        G.fe[j] = fe;
-        G.S[S_HVAL] = h_val;
-        G.S[S_RES] = fe;
-        int hl = G.I[I_HIST];
-        if (hl < G.hist_cap) G.hist[hl] = fe;
-        G.I[I_HIST] = hl + 1;
-        G.I[I_ITER] = G.I[I_ITER] + 1;
-        G.I[I_NOUT] = j + 1;                              // :389
-        const double tol = G.S[S_TOL];
-        bool conv = G.mf ? (h_val < tol || fe < tol) : (fe < tol);   // :172 / :385
-        if (!(fe == fe)) { G.I[I_BREAKDOWN] = 1; conv = true; }
-        if (conv) G.I[I_CONV_AT] = j;
-    }
-}
 
 __global__ void k_givens(const GmresDev G, const int j) {
     extern __shared__ double sm[];
     if (G.I[I_CONV_AT] >= 0) return;
-    givens_update_warp(G, j, G.S[S_RED], threadIdx.x, sm);
+    givens_update_warp(G, j, sqrt(G.S[S_RED]), threadIdx.x, sm);
 }
 
 // H(0..ncols-1, j) (+)= hvec   (gmres_mgsr.f90:351-353)
@@ -282,58 +216,10 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
     double accv[1] = {nacc};
     block_sum<1, kTsThreads>(accv, s_red);
     if (grid_sum<1>(accv, rc, gridDim.x, blockIdx.x, &s_flag)) {
-        if (fuse_givens && threadIdx.x < 32) givens_update_warp(G, j, rc.red[0], threadIdx.x, sm);
+        if (fuse_givens && threadIdx.x < 32) givens_update_warp(G, j, sqrt(rc.red[0]), threadIdx.x, sm);
     }
 }
 
-// ---- faithful MGS step (gmres_mgsr.f90:342-359), two loops fused in one pass:
-//   w -= h_prev * V_prev   (skipped when V_prev == nullptr)
-//   acc = V_cur . w        (skipped when V_cur == nullptr; then acc = ||w||^2 if want_norm)
-// post (last block): h = acc ; H(i_cur, j) += h ; S_TMP0 = h
-struct PMgsStep : PwBase<1> {
-    double *w;
-    const double *vprev, *vcur;
-    const double *S;
-    double hprev;
-    int want_norm;
-    __device__ __forceinline__ void init() { hprev = vprev ? S[S_TMP0] : 0.0; }
-    template <int VEC>
-    __device__ __forceinline__ void elem(size_t i, double *acc) const {
-        double a[VEC];
-        if (VEC == 2) {
-            double2 t = *reinterpret_cast<const double2 *>(w + i);
-            a[0] = t.x; a[VEC - 1] = t.y;
-        } else {
-            a[0] = w[i];
-        }
-        if (vprev) {
-            double p[VEC];
-            KL_LD(VEC, p, vprev, i)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) a[e] = fma(-hprev, p[e], a[e]);
-            KL_ST(VEC, w, i, a)
-        }
-        if (vcur) {
-            double q[VEC];
-            KL_LD(VEC, q, vcur, i)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], q[e], acc[0]);
-        } else if (want_norm) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], a[e], acc[0]);
-        }
-    }
-};
-struct PostMgs {
-    GmresDev G;
-    int j, i_cur;
-    __device__ __forceinline__ void run() const {
-        double h = G.S[S_RED];
-        G.S[S_TMP0] = h;
-        double *Hj = G.H + (size_t)j * G.ldh;
-        Hj[i_cur] = Hj[i_cur] + h;
-    }
-};
 struct PostBeta {   // gmres_mgsr.f90:322-323  beta = norm2(w) ; g(1) = beta
     GmresDev G;
     __device__ __forceinline__ void run() const {
@@ -479,6 +365,12 @@ int launch_wmvh(Ctx *c, const double *V, size_t ldv, double *w, size_t n, int nc
     return KL_OK;
 }
 
+int launch_backsolve(Ctx *c, const GmresDev &G) {
+    k_backsolve<<<1, 32, sizeof(double) * 2 * G.m, c->stream>>>(G);
+    c->stats.kernel_launches++;
+    return KL_OK;
+}
+
 // Gram-matrix epilogue shared with the Householder solver: G[c*(k)+i] = V_i . V_c, i <= c
 int gram_lower(Ctx *c, const double *V, size_t ldv, size_t n, int k, double *d_gram, std::vector<double> &out) {
     GmresDev none{};
@@ -505,6 +397,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
     const int ldh = m + 1;
     const int vec = (n % 2 == 0) ? 2 : 1;
     c->stats = kl_stats_t{};
+    prof_reset(c);
     cudaEvent_t evA, evB;
     KL_CUDA(c, cudaEventCreate(&evA));
     KL_CUDA(c, cudaEventCreate(&evB));
@@ -579,6 +472,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
             // V_j = w / norm ; z = A V_j   (:325-329 / :384 of the previous step ; :336).
             // omp: V_j is also written when the previous step converged (:384 precedes :385).
             if (fused) {
+                ProfScope ps(c, 0, "gmres_scale_apply (stencil: V_j=w/h; z=A V_j)", 24.0 * n);
                 Halo H;
                 const double *vecs[1] = {w};
                 KL_TRY(halo_exchange(&P, vecs, 1, &H));
@@ -595,8 +489,10 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
                 KL_TRY(op_apply(&P, Vj, z, true));
             }
             // w = M^-1 z (:337)
-            if (prec) KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
-            else std::swap(w, z);
+            if (prec) {
+                ProfScope ps(c, 1, "gmres_precond (stencil: w=M^-1 z)", 16.0 * n);
+                KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
+            } else std::swap(w, z);
             double *wj = w;
             const int ncols = j + 1;
             if (c->opt_ortho == KL_ORTHO_MGS2) {
@@ -620,10 +516,14 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
                 }
                 bytes += (32.0 * total + 24.0) * n;
             } else {
-                KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 1, true));
-                KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, false, G, j, false, true));
-                KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 2, true));
-                KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, true, G, j, true, true));
+                { ProfScope ps(c, 2, "gmres_vtw (h=V^T w tall-skinny projection)", (8.0 * ncols + 8.0) * n);
+                  KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 1, true)); }
+                { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
+                  KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, false, G, j, false, true)); }
+                { ProfScope ps(c, 2, "gmres_vtw (h=V^T w tall-skinny projection)", (8.0 * ncols + 8.0) * n);
+                  KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 2, true)); }
+                { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
+                  KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, true, G, j, true, true)); }
                 bytes += (32.0 * ncols + 48.0) * n;
             }
             bytes += (24.0 + (prec ? 16.0 : 0.0)) * n;
@@ -636,10 +536,10 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
             s.in = w; s.out = V + (size_t)m * ldv; s.S = c->d_S; s.s_idx = S_HVAL;
             KL_TRY(launch_pointwise(c, s, n, NoPost{}));
         }
-        k_backsolve<<<1, 32, sizeof(double) * 2 * m, c->stream>>>(G);                 // :394-398
+        KL_TRY(launch_backsolve(c, G));                                               // :394-398
         if (vec == 2) k_xpvy<2><<<upd_grid(n / 2), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
         else k_xpvy<1><<<upd_grid(n), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
-        c->stats.kernel_launches += 2;
+        c->stats.kernel_launches += 1;
         KL_TRY(read_back(c));
         n_out = c->h_pinned_i[I_NOUT];
         bytes += (8.0 * n_out + 16.0) * n;
@@ -685,6 +585,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
     KL_CUDA(c, cudaEventRecord(evB, c->stream));
     KL_CUDA(c, cudaStreamSynchronize(c->stream));
     KL_CUDA(c, cudaGetLastError());
+    prof_resolve(c);
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);

@@ -1,0 +1,453 @@
+// kl_hh.cu -- restarted GMRES with Walker's Householder orthogonalisation.
+//
+// Reference: src/gmres_hh.f90  gmres_hh_omp :211-385 (no preconditioner, no
+// in-cycle exit), gmres_hh_prec_omp :388-566 (left preconditioner, in-cycle
+// `converged` flag), calculate_verr :568-593.
+//
+// Data layout: the unit reflectors P are n x (m+1) column-major (ld = ldv);
+// reflector i is zero in rows < i.  H, g, cs, sn as in kl_gmres.cu.
+//
+// KL_HH_SEQUENTIAL (the reference's order): a reflector sweep v <- P_k ... P_i v
+// is a chain of point-wise kernels, each applying the previous reflector (axpy)
+// and accumulating the dot product with the next one in the same pass
+// (32n B per reflector instead of 40n).  The serial O(n) block of the reference
+// (:305-321) becomes: the last kernel of the sweep also reduces
+// sum_{t>j+1} w_t^2, one warp builds H(:,j), the Householder pivot and the Givens
+// update on the device, and one point-wise kernel writes the new reflector.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "kl_gmres.cuh"
+
+namespace kl {
+
+struct PostHh {   // S_TMP0 = 2 * dot   (the "2.0d0*P*dot" factor of gmres_hh.f90:280)
+    double *S;
+    __device__ __forceinline__ void run() const { S[S_TMP0] = 2.0 * S[S_RED]; }
+};
+
+// v = e_j - 2 P_j (P_j . e_j) fused with the dot against the next reflector
+// (gmres_hh.f90:257-283, first trip of the i-loop).
+struct PHhInit : PwBase<1> {
+    double *v;
+    const double *pj, *pnext;
+    long long j;
+    double d0;
+    __device__ __forceinline__ void init() { d0 = pj[j]; }
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *acc) const {
+        double p[VEC], a[VEC];
+        KL_LD(VEC, p, pj, i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            double ej = ((long long)(i + e) == j) ? 1.0 : 0.0;
+            a[e] = fma(-(2.0 * p[e]), d0, ej);
+        }
+        KL_ST(VEC, v, i, a)
+        if (pnext) {
+            double q[VEC];
+            KL_LD(VEC, q, pnext, i)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], q[e], acc[0]);
+        }
+    }
+};
+
+// w = [y(0..n_out-1); 0] fused with the dot against reflector n_out-1 (gmres_hh.f90:356-357)
+struct PHhLoadY : PwBase<1> {
+    double *w;
+    const double *y, *pnext;
+    long long n_out;
+    __device__ __forceinline__ void init() {}
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *acc) const {
+        double a[VEC], q[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = ((long long)(i + e) < n_out) ? y[i + e] : 0.0;
+        KL_ST(VEC, w, i, a)
+        KL_LD(VEC, q, pnext, i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[0] = fma(a[e], q[e], acc[0]);
+    }
+};
+
+// last trip of the second sweep: w -= 2 P_j (P_j.w) and S2 = sum_{t >= j+2} w_t^2
+struct PHhLast : PwBase<1> {
+    double *w;
+    const double *vprev;
+    const double *S;
+    long long tail0;   // first index of the tail sum (j+2); < 0: x += w instead (cycle end)
+    double *x;
+    double hprev;
+    __device__ __forceinline__ void init() { hprev = S[S_TMP0]; }
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *acc) const {
+        double a[VEC], p[VEC];
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(w + i);
+            a[0] = t.x; a[VEC - 1] = t.y;
+        } else {
+            a[0] = w[i];
+        }
+        KL_LD(VEC, p, vprev, i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = fma(-hprev, p[e], a[e]);
+        if (x) {   // gmres_hh.f90:374-378  x = x + w
+            double xv[VEC];
+            if (VEC == 2) {
+                double2 t = *reinterpret_cast<const double2 *>(x + i);
+                xv[0] = t.x; xv[VEC - 1] = t.y;
+            } else {
+                xv[0] = x[i];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xv[e] = xv[e] + a[e];
+            KL_ST(VEC, x, i, xv)
+        } else {
+            KL_ST(VEC, w, i, a)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if ((long long)(i + e) >= tail0) acc[0] = fma(a[e], a[e], acc[0]);
+        }
+    }
+};
+
+// new reflector P_{j+1} = w' / ||w'|| with w'(0..j) = 0, w'(j+1) = pivot' (gmres_hh.f90:315-318)
+struct PHhNewReflector : PwBase<0> {
+    const double *w;
+    double *p_out;
+    const double *S;
+    long long piv;   // index j+1 (0 for the first reflector of a cycle)
+    double nw, pv;
+    __device__ __forceinline__ void init() {
+        nw = S[S_NORM];
+        pv = S[S_TMP1];
+    }
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *) const {
+        double a[VEC];
+        KL_LD(VEC, a, w, i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            long long t = (long long)(i + e);
+            a[e] = t < piv ? 0.0 : ((t == piv ? pv : a[e]) / nw);
+        }
+        KL_ST(VEC, p_out, i, a)
+    }
+};
+
+// serial block of the reference by ONE WARP (gmres_hh.f90:305-345 / :486-526)
+__global__ void k_hh_step(const GmresDev G, const double *w, const int j, const int prec_variant) {
+    extern __shared__ double sm[];
+    if (G.I[I_CONV_AT] >= 0) return;
+    const int lane = threadIdx.x;
+    double *sh = sm;
+    double *Hj = G.H + (size_t)j * G.ldh;
+    for (int i = lane; i <= j; i += 32) {   // :306 H(1:j,j) = w(1:j)
+        double t = w[i];
+        sh[i] = t;
+        Hj[i] = t;
+    }
+    double hj1 = 0.0;
+    if (lane == 0) {
+        const double S2 = G.S[S_RED];
+        const double piv = w[j + 1];
+        const double tmp = sqrt(fma(piv, piv, S2));          // :308 norm2(w(j+1:n))
+        hj1 = (piv > 0.0) ? -tmp : tmp;                      // :309-313
+        const double pv = piv - hj1;                         // :316
+        G.S[S_TMP1] = pv;
+        G.S[S_NORM] = sqrt(fma(pv, pv, S2));                 // :317 norm2(w)
+    }
+    hj1 = __shfl_sync(0xffffffffu, hj1, 0);
+    __syncwarp();
+    const int conv_before = G.I[I_CONV_AT];
+    givens_update_warp(G, j, hj1, lane, sm, false);
+    if (lane == 0 && !prec_variant) {
+        // gmres_hh_omp: no in-cycle exit (:340-344 commented out)
+        if (G.I[I_BREAKDOWN] == 0) G.I[I_CONV_AT] = conv_before;
+    }
+}
+
+// first reflector of a cycle (gmres_hh.f90:250-253 / :433-436)
+__global__ void k_hh_first(const GmresDev G, const double *w) {
+    if (threadIdx.x != 0) return;
+    const double ss = G.S[S_RED];
+    const double w0 = w[0];
+    const double beta = sqrt(ss);
+    const double sg = copysign(beta, w0);
+    G.g[0] = -sg;                                            // :251
+    const double pv = sg + w0;                               // :252
+    double S2 = ss - w0 * w0;
+    if (S2 < 0.0) S2 = 0.0;
+    G.S[S_TMP1] = pv;
+    G.S[S_NORM] = sqrt(fma(pv, pv, S2));                     // :253 norm2(w)
+}
+
+struct HhRun {
+    Ctx *c;
+    Prob *P;
+    GmresDev G;
+    double *Pm;     // reflectors
+    size_t ldv, n;
+    double bytes;
+};
+
+// chain: v <- apply reflectors idx[0], idx[1], ... (in that order) to the vector already in `v`
+// whose dot with P_{first} is already in S_TMP0 (doubled).  Each kernel applies one reflector and
+// dots with the next.  The last one is returned to the caller (it has a special epilogue).
+static int hh_chain(HhRun &R, double *v, int first, int last, int dir, bool gated) {
+    // applies reflectors first, first+dir, ..., up to but NOT including `last`'s application:
+    // i.e. kernels for i = first .. last-dir, each: axpy(P_i) + dot(P_{i+dir})
+    Ctx *c = R.c;
+    for (int i = first; i != last; i += dir) {
+        PMgsStep s;
+        set_gate(s, c, gated);
+        s.w = v; s.S = c->d_S;
+        s.vprev = R.Pm + (size_t)i * R.ldv;
+        s.vcur = R.Pm + (size_t)(i + dir) * R.ldv;
+        s.want_norm = 0;
+        KL_TRY(launch_pointwise(c, s, R.n, PostHh{c->d_S}));
+        R.bytes += 32.0 * R.n;
+    }
+    return KL_OK;
+}
+
+static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m,
+                          double tol, double *final_err, double *v_err, int *n_out_p, int *stages_out_p,
+                          const kl_precond_t *M, const double *params, int nparams, int prec_variant) {
+    if (!c || !A || !b || !x || !final_err || !v_err || !n_out_p || !stages_out_p) return KL_ERR_INVALID;
+    if (m < 1 || m + 1 > kMaxCols) return c->fail(KL_ERR_INVALID, "restart length m out of range");
+    if (c->nranks > 1) return c->fail(KL_ERR_UNSUPPORTED, "Householder GMRES is single-GPU in this release");
+    Prob P;
+    KL_TRY(prob_init(&P, c, A, prec_variant ? M : nullptr, params, nparams, nx, ny));
+    const bool prec = P.pc.kind != KL_PC_NONE;
+    const size_t n = P.n;
+    if ((size_t)m + 1 >= n) return c->fail(KL_ERR_INVALID, "m must be smaller than the number of unknowns");
+    const size_t ldv = (n + 31) & ~size_t(31);
+    const int ldh = m + 1;
+    c->stats = kl_stats_t{};
+    cudaEvent_t evA, evB;
+    KL_CUDA(c, cudaEventCreate(&evA));
+    KL_CUDA(c, cudaEventCreate(&evB));
+    KL_CUDA(c, cudaEventRecord(evA, c->stream));
+    const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
+    size_t need = ws_need(ldv * (size_t)(m + 1)) + (c->opt_verr ? ws_need(ldv * (size_t)m) : 0) + 7 * ws_need(n) +
+                  ws_need((size_t)ldh * m) + 8 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
+    KL_TRY(ws_reserve(c, need));
+    ws_reset(c);
+    double *Pm = ws_take<double>(c, ldv * (size_t)(m + 1));
+    double *Vb = c->opt_verr ? ws_take<double>(c, ldv * (size_t)m) : nullptr;
+    double *w = ws_take<double>(c, n), *vj = ws_take<double>(c, n), *z = ws_take<double>(c, n);
+    double *aux = ws_take<double>(c, n), *aux2 = ws_take<double>(c, n);
+    double *db = dev ? const_cast<double *>(b) : ws_take<double>(c, n);
+    double *dx = dev ? x : ws_take<double>(c, n);
+    GmresDev G;
+    G.H = ws_take<double>(c, (size_t)ldh * m);
+    G.g = ws_take<double>(c, m + 2);
+    G.cs = ws_take<double>(c, m + 2);
+    G.sn = ws_take<double>(c, m + 2);
+    G.y = ws_take<double>(c, m + 2);
+    G.fe = ws_take<double>(c, m + 2);
+    G.hvec = ws_take<double>(c, m + 2);
+    double *d_gram = ws_take<double>(c, (size_t)(m + 2) * (m + 2));
+    G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
+    G.m = m; G.ldh = ldh; G.mf = 0;
+    HhRun R{c, &P, G, Pm, ldv, n, 0.0};
+
+    if (!dev) KL_TRY(stage_in(c, db, b, n));
+    KL_CUDA(c, cudaMemsetAsync(dx, 0, n * sizeof(double), c->stream));
+    KL_CUDA(c, cudaMemsetAsync(G.fe, 0, (m + 2) * sizeof(double), c->stream));
+    KL_CUDA(c, cudaMemsetAsync(c->d_I, 0, sizeof(int) * I_COUNT, c->stream));
+    {
+        double S0[48] = {0};
+        S0[S_TOL] = tol;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_S, S0, sizeof S0, cudaMemcpyHostToDevice, c->stream));
+        int m1 = -1;
+        KL_CUDA(c, cudaMemcpyAsync(c->d_I + I_CONV_AT, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    {   // beta0 = norm2(b) (:237)
+        PDot2 d;
+        set_gate(d, c, false);
+        d.a = db; d.b = db; d.c = nullptr; d.d = nullptr;
+        KL_TRY(launch_pointwise(c, d, n, PostStoreRed{c->d_S, S_BETA0, 1}));
+    }
+    KL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    const int max_stages = c->opt_max_restarts;
+    int status = KL_NOT_CONVERGED, n_out = 0, stages_out = 0, cycles = 0;
+    const size_t gsm = sizeof(double) * 3 * (m + 2);
+    for (int k = 1; k <= max_stages; ++k) {
+        ++cycles;
+        // g = 0 ; H = 0 (:241).  P = 0 is implicit: every reflector is fully written before use.
+        KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.cs, 0, sizeof(double) * (m + 2), c->stream));
+        KL_CUDA(c, cudaMemsetAsync(G.sn, 0, sizeof(double) * (m + 2), c->stream));
+        // w = b - A x [; w = M^-1 w] (:243-248 / :425-431)
+        if (prec) {
+            KL_TRY(op_resid(&P, dx, db, z, false));
+            KL_TRY(pc_apply(&P, z, w, aux, aux2, 1, false, NoPost{}));
+        } else {
+            KL_TRY(op_resid(&P, dx, db, w, false));
+            PDot2 d;
+            set_gate(d, c, false);
+            d.a = w; d.b = w; d.c = nullptr; d.d = nullptr;
+            KL_TRY(launch_pointwise(c, d, n, NoPost{}));
+        }
+        k_hh_first<<<1, 32, 0, c->stream>>>(G, w);           // :250-252
+        {
+            PHhNewReflector f;                                // :253 P(:,1) = w / norm2(w)
+            set_gate(f, c, false);
+            f.w = w; f.p_out = Pm; f.S = c->d_S; f.piv = 0;
+            KL_TRY(launch_pointwise(c, f, n, NoPost{}));
+        }
+        c->stats.kernel_launches++;
+        R.bytes += 56.0 * n;
+        for (int j = 0; j < m; ++j) {
+            // v = P_0 ... P_j e_j  (:257-283): reflectors applied in the order j, j-1, ..., 0
+            {
+                PHhInit f;
+                set_gate(f, c, true);
+                f.v = vj; f.pj = Pm + (size_t)j * ldv; f.pnext = j > 0 ? Pm + (size_t)(j - 1) * ldv : nullptr;
+                f.j = j;
+                KL_TRY(launch_pointwise(c, f, n, PostHh{c->d_S}));
+                R.bytes += (j > 0 ? 24.0 : 16.0) * n;
+            }
+            if (j > 0) {
+                KL_TRY(hh_chain(R, vj, j - 1, 0, -1, true));
+                // last: apply P_0 (no further dot)
+                PMgsStep s;
+                set_gate(s, c, true);
+                s.w = vj; s.S = c->d_S; s.vprev = Pm; s.vcur = nullptr; s.want_norm = 0;
+                KL_TRY(launch_pointwise(c, s, n, NoPost{}));
+                R.bytes += 24.0 * n;
+            }
+            // w = A v [; w = M^-1 w]  (:285 / :469-470)
+            if (prec) {
+                KL_TRY(op_apply(&P, vj, z, true));
+                KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
+                R.bytes += 32.0 * n;
+            } else {
+                KL_TRY(op_apply(&P, vj, w, true));
+                R.bytes += 16.0 * n;
+            }
+            // w = P_j ... P_0 w  (:290-304): order 0, 1, ..., j
+            {
+                PMgsStep s;   // dot with P_0 only
+                set_gate(s, c, true);
+                s.w = w; s.S = c->d_S; s.vprev = nullptr; s.vcur = Pm; s.want_norm = 0;
+                KL_TRY(launch_pointwise(c, s, n, PostHh{c->d_S}));
+                R.bytes += 16.0 * n;
+            }
+            KL_TRY(hh_chain(R, w, 0, j, +1, true));
+            {
+                PHhLast f;
+                set_gate(f, c, true);
+                f.w = w; f.vprev = Pm + (size_t)j * ldv; f.S = c->d_S; f.tail0 = (long long)j + 2; f.x = nullptr;
+                KL_TRY(launch_pointwise(c, f, n, NoPost{}));
+                R.bytes += 24.0 * n;
+            }
+            k_hh_step<<<1, 32, gsm, c->stream>>>(G, w, j, prec_variant);   // :305-345
+            c->stats.kernel_launches++;
+            {
+                PHhNewReflector f;                                          // :315-318
+                set_gate(f, c, true, j, 1);
+                f.w = w; f.p_out = Pm + (size_t)(j + 1) * ldv; f.S = c->d_S; f.piv = (long long)j + 1;
+                KL_TRY(launch_pointwise(c, f, n, NoPost{}));
+                R.bytes += 16.0 * n;
+            }
+        }
+        KL_TRY(launch_backsolve(c, G));                                    // :350-354
+        KL_TRY(read_back(c));
+        n_out = c->h_pinned_i[I_NOUT];
+        // w = [y;0] ; w = P_0 ... P_{n_out-1} w ; x += w  (:356-378)
+        {
+            PHhLoadY f;
+            set_gate(f, c, false);
+            f.w = w; f.y = G.y; f.pnext = Pm + (size_t)(n_out - 1) * ldv; f.n_out = n_out;
+            KL_TRY(launch_pointwise(c, f, n, PostHh{c->d_S}));
+            KL_TRY(hh_chain(R, w, n_out - 1, 0, -1, false));
+            PHhLast g;
+            set_gate(g, c, false);
+            g.w = w; g.vprev = Pm; g.S = c->d_S; g.tail0 = -1; g.x = dx;
+            KL_TRY(launch_pointwise(c, g, n, NoPost{}));
+            R.bytes += (32.0 * n_out + 24.0) * n;
+        }
+        stages_out = k;                                                    // :381
+        if (c->h_pinned_i[I_BREAKDOWN]) { status = KL_BREAKDOWN; break; }
+        if (c->h_pinned[S_RES] < tol) { status = KL_OK; break; }           // :382
+    }
+    KL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    KL_TRY(stage_out(c, x, dx, n));
+    KL_CUDA(c, cudaMemcpyAsync(final_err, G.fe, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    KL_TRY(fetch_history(c));
+    for (int i = 0; i <= m; ++i) v_err[i] = 0.0;
+    c->stats.orth_frobenius = NAN;
+    if (c->opt_verr && n_out >= 1) {
+        // calculate_verr (:568-593): V_i = P_0 ... P_i e_i, i < n_out
+        for (int i = 0; i < n_out; ++i) {
+            double *Vi = Vb + (size_t)i * ldv;
+            PHhInit f;
+            set_gate(f, c, false);
+            f.v = Vi; f.pj = Pm + (size_t)i * ldv; f.pnext = i > 0 ? Pm + (size_t)(i - 1) * ldv : nullptr;
+            f.j = i;
+            KL_TRY(launch_pointwise(c, f, n, PostHh{c->d_S}));
+            if (i > 0) {
+                KL_TRY(hh_chain(R, Vi, i - 1, 0, -1, false));
+                PMgsStep s;
+                set_gate(s, c, false);
+                s.w = Vi; s.S = c->d_S; s.vprev = Pm; s.vcur = nullptr; s.want_norm = 0;
+                KL_TRY(launch_pointwise(c, s, n, NoPost{}));
+            }
+        }
+        std::vector<double> gr;
+        KL_TRY(gram_lower(c, Vb, ldv, n, n_out, d_gram, gr));
+        double fro = 0.0;
+        for (int col = 0; col < n_out; ++col)
+            for (int i = 0; i <= col; ++i) {
+                double d = gr[(size_t)col * n_out + i] - (i == col ? 1.0 : 0.0);
+                fro += (i == col ? 1.0 : 2.0) * d * d;
+            }
+        c->stats.orth_frobenius = sqrt(fro);
+        for (int i = 1; i < n_out; ++i)                                   // :587-591
+            for (int jj = 0; jj < i; ++jj) {
+                double d = gr[(size_t)i * n_out + jj];
+                v_err[i] = v_err[i] + 2.0 * (d * d);
+            }
+    }
+    KL_CUDA(c, cudaEventRecord(evB, c->stream));
+    KL_CUDA(c, cudaStreamSynchronize(c->stream));
+    KL_CUDA(c, cudaGetLastError());
+    float ms = 0, ms_tot = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    cudaEventElapsedTime(&ms_tot, evA, evB);
+    cudaEventDestroy(evA);
+    cudaEventDestroy(evB);
+    c->stats.iterations = c->h_pinned_i[I_ITER];
+    c->stats.cycles = cycles;
+    c->stats.solve_ms = ms;
+    c->stats.total_ms = ms_tot;
+    c->stats.algorithmic_bytes = R.bytes;
+    *n_out_p = n_out;
+    *stages_out_p = stages_out;
+    return status;
+}
+
+}  // namespace kl
+
+using namespace kl;
+
+extern "C" {
+
+int kl_gmres_hh_omp(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m,
+                    double tol, double *final_err, double *v_err, int *n_out, int *stages_out) {
+    return gmres_hh_solve(h, A, b, x, nx, ny, m, tol, final_err, v_err, n_out, stages_out, nullptr, nullptr, 0, 0);
+}
+int kl_gmres_hh_prec_omp(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+                         int m, double tol, double *final_err, double *v_err, int *n_out, int *stages_out,
+                         const kl_precond_t *M, const double *params, int nparams) {
+    return gmres_hh_solve(h, A, b, x, nx, ny, m, tol, final_err, v_err, n_out, stages_out, M, params, nparams, 1);
+}
+
+}  // extern "C"

@@ -84,6 +84,7 @@ struct kl_context_s {
     int opt_use_graph = 1;
     int opt_hh_mode = KL_HH_SEQUENTIAL;
     int opt_fuse = 1;
+    int opt_profile = 0;
     // comm
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
@@ -107,6 +108,14 @@ struct kl_context_s {
     std::vector<double> history;
     int history_len = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // profiling (KL_OPT_PROFILE): event pairs per kernel class, resolved after the solve
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    const char *prof_name[KL_PROFILE_CLASSES] = {};
+    double prof_ms[KL_PROFILE_CLASSES] = {};
+    long long prof_launches[KL_PROFILE_CLASSES] = {};
+    double prof_bytes[KL_PROFILE_CLASSES] = {};
 
     int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
         char buf[512];
@@ -129,6 +138,17 @@ namespace kl {
         int r__ = (call);            \
         if (r__ < 0) return r__;     \
     } while (0)
+
+// profiling helpers (kl_core.cu)
+void prof_reset(Ctx *c);
+void prof_begin(Ctx *c, int cls, const char *name, double bytes);
+void prof_end(Ctx *c);
+void prof_resolve(Ctx *c);
+struct ProfScope {
+    Ctx *c;
+    ProfScope(Ctx *c_, int cls, const char *name, double bytes) : c(c_) { if (c->opt_profile) prof_begin(c, cls, name, bytes); }
+    ~ProfScope() { if (c->opt_profile) prof_end(c); }
+};
 
 // workspace arena
 int ws_reserve(Ctx *c, size_t bytes);

@@ -109,7 +109,8 @@ enum {
     KL_OPT_CHECK_EVERY = 4,   /* CG/BiCGSTAB: iterations enqueued between host polls (default 32) */
     KL_OPT_USE_GRAPH = 5,     /* 1 (default): replay iterations from a CUDA graph    */
     KL_OPT_HH_MODE = 6,       /* Householder application, see below                  */
-    KL_OPT_FUSE = 7           /* 1 (default): fused kernels; 0: one kernel per reference loop */
+    KL_OPT_FUSE = 7,          /* 1 (default): fused kernels; 0: one kernel per reference loop */
+    KL_OPT_PROFILE = 8        /* 1: CUDA-event pairs around every hot kernel (kl_get_profile)  */
 };
 enum {
     KL_ORTHO_MGS2 = 0,  /* the reference's modified Gram-Schmidt applied twice (gmres_mgsr.f90:341-360) */
@@ -220,6 +221,11 @@ typedef struct {
     double h2d_bytes, d2h_bytes;
 } kl_stats_t;
 int kl_get_stats(kl_handle_t h, kl_stats_t *out);
+/* per-kernel-class timers of the last solve (KL_OPT_PROFILE = 1): class idx in
+ * [0, KL_PROFILE_CLASSES); name may be NULL.  Returns KL_ERR_INVALID past the end. */
+#define KL_PROFILE_CLASSES 8
+int kl_get_profile(kl_handle_t h, int idx, const char **name, double *ms, long long *launches,
+                   double *algorithmic_bytes);
 
 #ifdef __cplusplus
 }

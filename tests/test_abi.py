@@ -1,0 +1,68 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/krylov_b200.h declares,
+and refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "krylov_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(kl_[a-z0-9_]+)\s*\(", hdr)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import gmres_b200 as kl
+    path = kl.library_path()
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(path)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_reference_entry_points_present(lib):
+    # one entry per public module procedure of the reference
+    for n in ("kl_gmres_mgsr_omp", "kl_gmres_mgsr_mf", "kl_gmres_hh_omp", "kl_gmres_hh_prec_omp", "kl_cg",
+              "kl_pcg", "kl_cg_omp", "kl_pcg_omp", "kl_bicgstab", "kl_pbicgstab", "kl_pbicgstab_omp",
+              "kl_apply_operator", "kl_apply_precond"):
+        assert hasattr(lib, n)
+
+
+def test_no_cpu_fallback():
+    import torch
+    import gmres_b200 as kl
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(kl.KrylovError):
+        kl.Handle(0)
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under gmres_b200/ may import, link or load oracle/."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "gmres_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".f90", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"libkrylov_oracle|from oracle|import oracle|\bko_[a-z]+\s*\(|dlopen\([^)]*oracle", txt):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_cheb_params_policy(lib):
+    out = (ctypes.c_double * 2)()
+    lib.kl_cheb_params_from_ritz.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    assert lib.kl_cheb_params_from_ritz(0.01, 8.0, out) == 0
+    assert out[0] == pytest.approx(8.2) and out[1] == pytest.approx(0.2)   # tests/test_poisson_mf.f90:38
