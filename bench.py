@@ -250,7 +250,7 @@ def gpu_arm(args):
     if world == 1 and args.extras:
         for name, st in (("gmres4096", 95), ("pcg16384", args.steps), ("bicgstab8192", args.steps),
                          ("hh1024", 95), ("gmres300", 475)):
-            if name == args.workload:
+            if name == args.workload or (args.only_extras and name not in args.only_extras.split(",")):
                 continue
             try:
                 e = measure(name, st, st if WORKLOADS[name]["m"] else 3, False, True)
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cg16384", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", dest="extras", action="store_false")
+    ap.add_argument("--only-extras", default="", help="comma-separated subset of the extra workloads")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

@@ -26,36 +26,27 @@ struct FBiDir : StencilBase<3, (CB ? 0 : 1)> {
     const double *r0;
     const double *S;
     double beta, omega, d, calpha;
+    FastDiv fd;
     __device__ __forceinline__ void init() {
         beta = S[S_BETA];
         omega = S[S_OMEGA];
+        fd.set(d);
     }
     __device__ __forceinline__ double pn(double r, double p, double ap) const {
         return fma(beta, fma(-omega, ap, p), r);     // bicgstab.f90:176
     }
-    template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[3], int i, double (&u)[VEC]) const {
-        double vr[VEC], vp[VEC], va[VEC];
-        KL_LD(VEC, vr, rp[0], i)
-        KL_LD(VEC, vp, rp[1], i)
-        KL_LD(VEC, va, rp[2], i)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            double t = pn(vr[v], vp[v], va[v]);
-            u[v] = CB ? t / d : t;
-        }
+    __device__ __forceinline__ double point(const double (&v)[3]) const {
+        const double t = pn(v[0], v[1], v[2]);
+        return CB ? fd.div(t) : t;
     }
     template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[3][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
         if (CB) {
-            double vr[VEC], vp[VEC], va[VEC], pv[VEC], zv[VEC];
-            KL_LD(VEC, vr, this->in[0], idx)
-            KL_LD(VEC, vp, this->in[1], idx)
-            KL_LD(VEC, va, this->in[2], idx)
+            double pv[VEC], zv[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                pv[v] = pn(vr[v], vp[v], va[v]);
+                pv[v] = pn(raw[0][v], raw[1][v], raw[2][v]);
                 zv[v] = fma(calpha, pv[v] - au[v], cu[v]);   // chebyshev.f90:35
             }
             KL_ST(VEC, p_new, idx, pv)
@@ -77,28 +68,20 @@ struct FBiS : StencilBase<2, (CB ? 0 : 2)> {
     double *s, *out;       // out = as (CB = false) or z2 (CB = true)
     const double *S;
     double alpha, d, calpha;
-    __device__ __forceinline__ void init() { alpha = S[S_ALPHA]; }
-    template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[2], int i, double (&u)[VEC]) const {
-        double vr[VEC], va[VEC];
-        KL_LD(VEC, vr, rp[0], i)
-        KL_LD(VEC, va, rp[1], i)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            double t = fma(-alpha, va[v], vr[v]);    // bicgstab.f90:134
-            u[v] = CB ? t / d : t;
-        }
+    FastDiv fd;
+    __device__ __forceinline__ void init() { alpha = S[S_ALPHA]; fd.set(d); }
+    __device__ __forceinline__ double point(const double (&v)[2]) const {
+        const double t = fma(-alpha, v[1], v[0]);    // bicgstab.f90:134
+        return CB ? fd.div(t) : t;
     }
     template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
         if (CB) {
-            double vr[VEC], va[VEC], sv[VEC], zv[VEC];
-            KL_LD(VEC, vr, this->in[0], idx)
-            KL_LD(VEC, va, this->in[1], idx)
+            double sv[VEC], zv[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                sv[v] = fma(-alpha, va[v], vr[v]);
+                sv[v] = fma(-alpha, raw[1][v], raw[0][v]);
                 zv[v] = fma(calpha, sv[v] - au[v], cu[v]);
             }
             KL_ST(VEC, s, idx, sv)
@@ -219,6 +202,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     const size_t n = P.n;
     const int maxit = *iter;
     c->stats = kl_stats_t{};
+    prof_reset(c);
     cudaEvent_t evA, evB;
     KL_CUDA(c, cudaEventCreate(&evA));
     KL_CUDA(c, cudaEventCreate(&evB));

@@ -2,6 +2,9 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "kl_internal.cuh"
 
 namespace kl {
@@ -20,6 +23,40 @@ int ws_reserve(Ctx *c, size_t bytes) {
         return c->fail(KL_ERR_ALLOC, "workspace cudaMalloc", e);
     }
     c->ws_bytes = bytes;
+    return KL_OK;
+}
+
+// 2-D FP64 tensor map over an nx x ny grid (i fastest), box = 256 columns x kTmaSR lines, zero fill
+// outside the grid.  Descriptors are cached per (pointer, extents); cuTensorMapEncodeTiled is taken
+// from the driver through the runtime so that libcuda is not a link-time dependency.
+int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    for (auto &e : c->tmaps)
+        if (e.base == base && e.nx == nx && e.ny == ny) {
+            memcpy(out, e.blob, sizeof(CUtensorMap));
+            return KL_OK;
+        }
+    if (!c->encode_fn) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled entry point", e);
+        c->encode_fn = fn;
+    }
+    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
+    cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)kTmaBoxX, (cuuint32_t)kTmaSR};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (c->tmaps.size() >= 256) c->tmaps.clear();
+    Ctx::TmapEntry e;
+    e.base = base; e.nx = nx; e.ny = ny;
+    memcpy(e.blob, out, sizeof(CUtensorMap));
+    c->tmaps.push_back(e);
     return KL_OK;
 }
 
@@ -266,6 +303,7 @@ int kl_set_option(kl_handle_t h, int key, int value) {
             break;
         case KL_OPT_FUSE: h->opt_fuse = value != 0; break;
         case KL_OPT_PROFILE: h->opt_profile = value != 0; break;
+        case KL_OPT_TMA: h->opt_tma = value != 0; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;
@@ -282,6 +320,7 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_HH_MODE: *value = h->opt_hh_mode; break;
         case KL_OPT_FUSE: *value = h->opt_fuse; break;
         case KL_OPT_PROFILE: *value = h->opt_profile; break;
+        case KL_OPT_TMA: *value = h->opt_tma; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;

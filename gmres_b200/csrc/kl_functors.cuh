@@ -19,63 +19,48 @@ inline Cbpr2Coef cbpr2_coef(const double *params) {
 }
 
 // ---------------------------------------------------------------------------
-// stencil functors
+// stencil functors (contract: kl_internal.cuh, k_stencil)
 // ---------------------------------------------------------------------------
+#define KL_ST(VEC, ptr, idx, src)                            \
+    if (VEC == 2) stg2((ptr) + (idx), src[0], src[VEC - 1]); \
+    else (ptr)[idx] = src[0];
+#define KL_LD(VEC, dst, ptr, idx)                         \
+    if (VEC == 2) {                                       \
+        double2 t__ = ldg2((ptr) + (idx));                \
+        dst[0] = t__.x;                                   \
+        dst[VEC - 1] = t__.y;                             \
+    } else {                                              \
+        dst[0] = __ldg((ptr) + (idx));                    \
+    }
 
 // y = A x                                     (poisson.f90:33-77)
 struct FApply : StencilBase<1, 0> {
     double *y;
     __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return v[0]; }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = a.x;
-            u[VEC - 1] = a.y;
-        } else {
-            u[0] = __ldg(rp[0] + i);
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *) const {
-        if (VEC == 2) stg2(y + idx, au[0], au[VEC - 1]);
-        else y[idx] = au[0];
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *) const {
+        KL_ST(VEC, y, idx, au)
     }
 };
 
 // y = A x with two fused dot products:
-//   acc0 = sum (A x) * e1 ; acc1 = e2 ? sum (A x) * e2 : sum (A x)^2
-// (bicgstab.f90:123-127 ap.r0 with r.r0 ; :139-143 as.s, as.as ; cg.f90:118-122)
+//   acc0 = sum (A x) * e1 ; acc1 = self2 ? sum (A x)^2 : sum (A x) * e2
+// (bicgstab.f90:123-127 ap.r0 ; :139-143 as.s, as.as)
 struct FApplyDots : StencilBase<1, 2> {
     double *y;
     const double *e1, *e2;
-    int self2;  // acc1 = sum (Ax)^2
+    int self2;
     __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return v[0]; }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = a.x;
-            u[VEC - 1] = a.y;
-        } else {
-            u[0] = __ldg(rp[0] + i);
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
         double a1[VEC], a2[VEC];
-        if (VEC == 2) {
-            stg2(y + idx, au[0], au[VEC - 1]);
-            double2 t = ldg2(e1 + idx);
-            a1[0] = t.x; a1[VEC - 1] = t.y;
-            if (!self2) { double2 s = ldg2(e2 + idx); a2[0] = s.x; a2[VEC - 1] = s.y; }
-        } else {
-            y[idx] = au[0];
-            a1[0] = __ldg(e1 + idx);
-            if (!self2) a2[0] = __ldg(e2 + idx);
-        }
+        KL_ST(VEC, y, idx, au)
+        KL_LD(VEC, a1, e1, idx)
+        if (!self2) { KL_LD(VEC, a2, e2, idx) }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             acc[0] = fma(au[v], a1[v], acc[0]);
@@ -89,25 +74,15 @@ struct FResid : StencilBase<1, 0> {
     const double *b;
     double *z;
     __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return v[0]; }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = a.x;
-            u[VEC - 1] = a.y;
-        } else {
-            u[0] = __ldg(rp[0] + i);
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *) const {
-        if (VEC == 2) {
-            double2 bb = ldg2(b + idx);
-            stg2(z + idx, bb.x - au[0], bb.y - au[VEC - 1]);
-        } else {
-            z[idx] = __ldg(b + idx) - au[0];
-        }
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *) const {
+        double bb[VEC];
+        KL_LD(VEC, bb, b, idx)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) bb[v] = bb[v] - au[v];
+        KL_ST(VEC, z, idx, bb)
     }
 };
 
@@ -119,35 +94,21 @@ template <int MODE>
 struct FCbpr2 : StencilBase<1, (MODE ? 1 : 0)> {
     double *z;
     double d, alpha;
-    __device__ __forceinline__ void init() {}
+    FastDiv fd;
+    __device__ __forceinline__ void init() { fd.set(d); }
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return fd.div(v[0]); }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = a.x / d;
-            u[VEC - 1] = a.y / d;
-        } else {
-            u[0] = __ldg(rp[0] + i) / d;
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
-        double rr[VEC], zz[VEC];
-        if (VEC == 2) {
-            double2 t = ldg2(this->in[0] + idx);
-            rr[0] = t.x; rr[VEC - 1] = t.y;
-        } else {
-            rr[0] = __ldg(this->in[0] + idx);
-        }
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        double zz[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            zz[v] = fma(alpha, rr[v] - au[v], cu[v]);
+            const double rr = raw[0][v];
+            zz[v] = fma(alpha, rr - au[v], cu[v]);
             if (MODE == 1) acc[0] = fma(zz[v], zz[v], acc[0]);
-            if (MODE == 2) acc[0] = fma(rr[v], zz[v], acc[0]);
+            if (MODE == 2) acc[0] = fma(rr, zz[v], acc[0]);
         }
-        if (VEC == 2) stg2(z + idx, zz[0], zz[VEC - 1]);
-        else z[idx] = zz[0];
+        KL_ST(VEC, z, idx, zz)
     }
 };
 
@@ -161,26 +122,12 @@ struct FCgDir : StencilBase<2, 1> {
     const double *S;
     double beta;
     __device__ __forceinline__ void init() { beta = S[S_BETA]; }
+    __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[2], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 zz = ldg2(rp[0] + i), pp = ldg2(rp[1] + i);
-            u[0] = fma(beta, pp.x, zz.x);
-            u[VEC - 1] = fma(beta, pp.y, zz.y);
-        } else {
-            u[0] = fma(beta, __ldg(rp[1] + i), __ldg(rp[0] + i));
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
-        if (VEC == 2) {
-            stg2(p_new + idx, cu[0], cu[VEC - 1]);
-            stg2(ax + idx, au[0], au[VEC - 1]);
-        } else {
-            p_new[idx] = cu[0];
-            ax[idx] = au[0];
-        }
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        KL_ST(VEC, p_new, idx, cu)
+        KL_ST(VEC, ax, idx, au)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[0] = fma(au[v], cu[v], acc[0]);
     }
@@ -192,46 +139,20 @@ struct FScaleApply : StencilBase<1, 0> {
     double *v_out, *z;
     const double *S;
     int s_idx;
-    double s;
-    __device__ __forceinline__ void init() { s = S[s_idx]; }
+    FastDiv fd;
+    __device__ __forceinline__ void init() { fd.set(S[s_idx]); }
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return fd.div(v[0]); }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = a.x / s;
-            u[VEC - 1] = a.y / s;
-        } else {
-            u[0] = __ldg(rp[0] + i) / s;
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *) const {
-        if (VEC == 2) {
-            stg2(v_out + idx, cu[0], cu[VEC - 1]);
-            stg2(z + idx, au[0], au[VEC - 1]);
-        } else {
-            v_out[idx] = cu[0];
-            z[idx] = au[0];
-        }
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *) const {
+        KL_ST(VEC, v_out, idx, cu)
+        KL_ST(VEC, z, idx, au)
     }
 };
 
 // ---------------------------------------------------------------------------
 // point-wise functors
 // ---------------------------------------------------------------------------
-#define KL_LD(VEC, dst, ptr, idx)                         \
-    if (VEC == 2) {                                       \
-        double2 t__ = ldg2((ptr) + (idx));                \
-        dst[0] = t__.x;                                   \
-        dst[VEC - 1] = t__.y;                             \
-    } else {                                              \
-        dst[0] = __ldg((ptr) + (idx));                    \
-    }
-#define KL_ST(VEC, ptr, idx, src)                         \
-    if (VEC == 2) stg2((ptr) + (idx), src[0], src[VEC - 1]); \
-    else (ptr)[idx] = src[0];
-
 // acc0 = sum a*b ; acc1 = sum c*d   (c == nullptr => only one)
 struct PDot2 : PwBase<2> {
     const double *a, *b, *c, *d;
@@ -259,14 +180,14 @@ struct PScale : PwBase<0> {
     double *out;
     const double *S;
     int s_idx;
-    double s;
-    __device__ __forceinline__ void init() { s = S[s_idx]; }
+    FastDiv fd;
+    __device__ __forceinline__ void init() { fd.set(S[s_idx]); }
     template <int VEC>
     __device__ __forceinline__ void elem(size_t i, double *) const {
         double v[VEC];
         KL_LD(VEC, v, in, i)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = v[k] / s;
+        for (int k = 0; k < VEC; ++k) v[k] = fd.div(v[k]);
         KL_ST(VEC, out, i, v)
     }
 };

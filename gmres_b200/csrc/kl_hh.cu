@@ -120,9 +120,10 @@ struct PHhNewReflector : PwBase<0> {
     double *p_out;
     const double *S;
     long long piv;   // index j+1 (0 for the first reflector of a cycle)
-    double nw, pv;
+    double pv;
+    FastDiv fd;
     __device__ __forceinline__ void init() {
-        nw = S[S_NORM];
+        fd.set(S[S_NORM]);
         pv = S[S_TMP1];
     }
     template <int VEC>
@@ -132,7 +133,7 @@ struct PHhNewReflector : PwBase<0> {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             long long t = (long long)(i + e);
-            a[e] = t < piv ? 0.0 : ((t == piv ? pv : a[e]) / nw);
+            a[e] = t < piv ? 0.0 : fd.div(t == piv ? pv : a[e]);
         }
         KL_ST(VEC, p_out, i, a)
     }
@@ -228,6 +229,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     const size_t ldv = (n + 31) & ~size_t(31);
     const int ldh = m + 1;
     c->stats = kl_stats_t{};
+    prof_reset(c);
     cudaEvent_t evA, evB;
     KL_CUDA(c, cudaEventCreate(&evA));
     KL_CUDA(c, cudaEventCreate(&evB));

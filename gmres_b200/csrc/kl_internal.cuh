@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,8 @@ struct kl_context_s {
     int opt_hh_mode = KL_HH_SEQUENTIAL;
     int opt_fuse = 1;
     int opt_profile = 0;
+    int opt_tma = 1;
+    int opt_stencil_rows = 0;   // 0: heuristic
     // comm
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
@@ -108,6 +111,10 @@ struct kl_context_s {
     std::vector<double> history;
     int history_len = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // TMA descriptor cache (opaque 128-byte CUtensorMap blobs keyed by base pointer and extents)
+    struct TmapEntry { const void *base; int nx, ny; alignas(64) unsigned char blob[128]; };
+    std::vector<TmapEntry> tmaps;
+    void *encode_fn = nullptr;
     // profiling (KL_OPT_PROFILE): event pairs per kernel class, resolved after the solve
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
@@ -177,6 +184,43 @@ __device__ __forceinline__ double2 ldg2(const double *p) {
 __device__ __forceinline__ void stg2(double *p, double a, double b) {
     *reinterpret_cast<double2 *>(p) = make_double2(a, b);
 }
+
+// Correctly rounded x/d for a divisor that is constant over the kernel.
+// The hardware sequence (MUFU.RCP64H + Newton steps + range check per element)
+// makes division-carrying stencil kernels instruction-bound; with the reciprocal
+// hoisted, Markstein's correction  q <- q + (x - q d) * rd  applied twice gives
+// the IEEE-754 quotient in 5 FMA-class instructions (rd = RN(1/d); exact when no
+// underflow/overflow occurs and the significand of d is not all ones -- those
+// cases fall back to the hardware division).  Bit-compatibility with the
+// reference's r(i)/d is verified in tests/test_gpu_parity.py.
+static __device__ __noinline__ double slow_div(double x, double d) { return x / d; }
+struct FastDiv {
+    double d, rd;
+    int ok;
+    __host__ __device__ __forceinline__ void set(double dd) {
+        d = dd;
+        rd = 1.0 / dd;
+        unsigned long long bits;
+#ifdef __CUDA_ARCH__
+        bits = (unsigned long long)__double_as_longlong(dd);
+#else
+        memcpy(&bits, &dd, sizeof bits);
+#endif
+        const unsigned long long man = bits & 0x000fffffffffffffULL;
+        const int ex = (int)((bits >> 52) & 0x7ff);
+        ok = (man != 0x000fffffffffffffULL) && ex > 200 && ex < 1800;
+    }
+    __device__ __forceinline__ double div(double x) const {
+        const double q0 = x * rd;
+        double r = fma(-q0, d, x);
+        double q = fma(r, rd, q0);
+        r = fma(-q, d, x);
+        q = fma(r, rd, q);
+        const double ax = fabs(x);
+        if (!(ok && ax >= 0x1p-700 && ax <= 0x1p700)) q = (x == 0.0 && ok) ? q0 : slow_div(x, d);
+        return q;
+    }
+};
 
 // Block-level reduction of K values, deterministic; result valid in thread 0.
 template <int K, int NT>
@@ -299,6 +343,15 @@ struct StencilBase {
 
 constexpr int kStencilThreads = 128;
 
+// Functor contract (see kl_functors.cuh):
+//   double point(const double (&v)[NIN]) const      u at one grid point from the NIN raw inputs
+//   template<int VEC> void store(size_t idx, const double (&raw)[NIN][VEC],
+//                                const double (&cu)[VEC], const double (&au)[VEC], double *acc) const
+// The kernel owns all loads: raw input lines are fetched kPf lines ahead of their
+// use (software pipeline in registers) so that each thread keeps several
+// independent 16-byte loads in flight; point() runs when a line is consumed.
+constexpr int kPf = 2;   // prefetch distance in grid lines
+
 template <class F, int OPK, int VEC, class Post>
 __global__ void __launch_bounds__(kStencilThreads)
 k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post) {
@@ -307,61 +360,94 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
     f.init();
     constexpr int NIN = F::NIN;
     constexpr int NRED = F::NRED;
+    constexpr int NR = NRED > 0 ? NRED : 1;
     const int lane = threadIdx.x & 31;
     const int i0 = (blockIdx.x * kStencilThreads + threadIdx.x) * VEC;
     const bool act = i0 < g.nx;
+    const bool has_l = act && lane == 0 && i0 > 0;
+    const bool has_r = act && lane == 31 && i0 + VEC < g.nx;
     const int j0 = blockIdx.y * g.rows;
     const int j1 = min(j0 + g.rows, g.ny);
-    double acc[NRED > 0 ? NRED : 1];
+    double acc[NR];
 #pragma unroll
-    for (int k = 0; k < (NRED > 0 ? NRED : 1); ++k) acc[k] = 0.0;
+    for (int k = 0; k < NR; ++k) acc[k] = 0.0;
 
-    auto rowptrs = [&](int j, const double *(&rp)[NIN]) -> bool {
-        if (j < 0) {
-            if (f.lo[0] == nullptr) return false;
-#pragma unroll
-            for (int a = 0; a < NIN; ++a) rp[a] = f.lo[a];
-        } else if (j >= g.ny) {
-            if (f.hi[0] == nullptr) return false;
-#pragma unroll
-            for (int a = 0; a < NIN; ++a) rp[a] = f.hi[a];
-        } else {
-#pragma unroll
-            for (int a = 0; a < NIN; ++a) rp[a] = f.in[a] + (size_t)j * g.nx;
-        }
-        return true;
+    struct Raw {
+        double c[NIN][VEC];
+        double l[NIN], r[NIN];
+        bool ok;
     };
-    auto load_row = [&](int j, double (&u)[VEC]) {
+    // raw loads of line j (may be a halo line or outside the domain)
+    auto load_raw = [&](int j, Raw &R) {
         const double *rp[NIN];
-        if (act && rowptrs(j, rp)) {
-            f.template eval<VEC>(rp, i0, u);
-        } else {
+        bool ok = act && j <= j1;
+        if (ok) {
+            if (j < 0) {
+                ok = f.lo[0] != nullptr;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) u[v] = 0.0;
-        }
-    };
-
-    double up[VEC], cu[VEC], dn[VEC];
-    load_row(j0 - 1, up);
-    load_row(j0, cu);
-#pragma unroll 2
-    for (int j = j0; j < j1; ++j) {
-        load_row(j + 1, dn);
-        double l = __shfl_up_sync(0xffffffffu, cu[VEC - 1], 1);
-        double r = __shfl_down_sync(0xffffffffu, cu[0], 1);
-        if (lane == 0 || lane == 31) {
-            const double *rp[NIN];
-            rowptrs(j, rp);
-            if (lane == 0) {
-                double t[1] = {0.0};
-                if (act && i0 > 0) f.template eval<1>(rp, i0 - 1, t);
-                l = t[0];
+                for (int a = 0; a < NIN; ++a) rp[a] = f.lo[a];
+            } else if (j >= g.ny) {
+                ok = f.hi[0] != nullptr;
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) rp[a] = f.hi[a];
             } else {
-                double t[1] = {0.0};
-                if (act && i0 + VEC < g.nx) f.template eval<1>(rp, i0 + VEC, t);
-                r = t[0];
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) rp[a] = f.in[a] + (size_t)j * g.nx;
             }
         }
+        R.ok = ok;
+#pragma unroll
+        for (int a = 0; a < NIN; ++a) {
+            if (ok) {
+                if (VEC == 2) {
+                    double2 t = ldg2(rp[a] + i0);
+                    R.c[a][0] = t.x;
+                    R.c[a][VEC - 1] = t.y;
+                } else {
+                    R.c[a][0] = __ldg(rp[a] + i0);
+                }
+            } else {
+                R.c[a][0] = 0.0;
+                R.c[a][VEC - 1] = 0.0;
+            }
+            R.l[a] = (ok && has_l) ? __ldg(rp[a] + i0 - 1) : 0.0;
+            R.r[a] = (ok && has_r) ? __ldg(rp[a] + i0 + VEC) : 0.0;
+        }
+    };
+    // u of a line from its raw inputs (+ the two warp-edge neighbours)
+    auto compute = [&](const Raw &R, double (&u)[VEC], double &ul, double &ur) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            double t[NIN];
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) t[a] = R.c[a][v];
+            u[v] = R.ok ? f.point(t) : 0.0;
+        }
+        ul = (R.ok && has_l) ? f.point(R.l) : 0.0;
+        ur = (R.ok && has_r) ? f.point(R.r) : 0.0;
+    };
+
+    Raw rawA, rawB, rawCu, rawDn;
+    double up[VEC], cu[VEC], dn[VEC], cl, cr, dl, dr, tl, tr;
+    {
+        Raw t;
+        load_raw(j0 - 1, t);
+        load_raw(j0, rawCu);
+        load_raw(j0 + 1, rawA);
+        load_raw(j0 + 2, rawB);
+        compute(t, up, tl, tr);
+        compute(rawCu, cu, cl, cr);
+    }
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        Raw rawN;
+        load_raw(j + 1 + kPf, rawN);          // prefetch, consumed kPf lines later
+        compute(rawA, dn, dl, dr);
+        rawDn = rawA;
+        double l = __shfl_up_sync(0xffffffffu, cu[VEC - 1], 1);
+        double r = __shfl_down_sync(0xffffffffu, cu[0], 1);
+        if (lane == 0) l = cl;
+        if (lane == 31) r = cr;
         if (act) {
             double au[VEC];
             if (VEC == 1) {
@@ -370,20 +456,25 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
                 au[0] = apply5<OPK>(cu[0], l, cu[VEC - 1], dn[0], up[0], f.coef);
                 au[VEC - 1] = apply5<OPK>(cu[VEC - 1], cu[0], r, dn[VEC - 1], up[VEC - 1], f.coef);
             }
-            f.template store<VEC>((size_t)j * g.nx + i0, cu, au, acc);
+            f.template store<VEC>((size_t)j * g.nx + i0, rawCu.c, cu, au, acc);
         }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             up[v] = cu[v];
             cu[v] = dn[v];
         }
+        cl = dl;
+        cr = dr;
+        rawCu = rawDn;
+        rawA = rawB;
+        rawB = rawN;
     }
     if (NRED > 0) {
-        __shared__ double sm[(NRED > 0 ? NRED : 1) * (kStencilThreads / 32)];
+        __shared__ double sm[NR * (kStencilThreads / 32)];
         __shared__ int s_flag;
-        block_sum<(NRED > 0 ? NRED : 1), kStencilThreads>(acc, sm);
+        block_sum<NR, kStencilThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        if (grid_sum<(NRED > 0 ? NRED : 1)>(acc, rc, nb, bid, &s_flag)) {
+        if (grid_sum<NR>(acc, rc, nb, bid, &s_flag)) {
             if (fuse_post && threadIdx.x == 0) post.run();
         }
     }
@@ -471,11 +562,17 @@ inline int finish_reduction(Ctx *c, int nred, const Post &post) {
     return KL_OK;
 }
 
+}  // namespace kl
+#include "kl_stencil_tma.cuh"
+namespace kl {
+
 template <class F, class Post>
 inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, const Post &post) {
     const int vec = (nx % 2 == 0) ? 2 : 1;
+    const bool tma = c->opt_tma && vec == 2 && nx >= 64;
+    const int strip = tma ? kTmaStrip : kStencilThreads * vec;
     Geo g{nx, ny, stencil_rows(nx, ny, vec)};
-    dim3 grid((nx + kStencilThreads * vec - 1) / (kStencilThreads * vec), (ny + g.rows - 1) / g.rows);
+    dim3 grid((nx + strip - 1) / strip, (ny + g.rows - 1) / g.rows);
     if ((long)grid.x * grid.y > kMaxBlocks) {
         g.rows = (int)(((long)ny * grid.x + kMaxBlocks - 1) / kMaxBlocks);
         grid.y = (ny + g.rows - 1) / g.rows;
@@ -483,10 +580,23 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
     const int fuse = c->nranks == 1;
-#define KL_ST_LAUNCH(OPK)                                                                         \
-    if (vec == 2)                                                                                 \
-        k_stencil<F, OPK, 2, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse); \
-    else                                                                                          \
+    TMaps<F::NIN> tm;
+    if (tma) {
+        for (int a = 0; a < F::NIN; ++a) KL_TRY(tmap_encode(c, &tm.m[a], f.in[a], nx, ny));
+    }
+    constexpr size_t smem = tma_smem_bytes<F::NIN>();
+#define KL_ST_LAUNCH(OPK)                                                                           \
+    if (tma) {                                                                                      \
+        static bool attr_done = false;                                                              \
+        if (!attr_done) {                                                                           \
+            cudaFuncSetAttribute(k_stencil_tma<F, OPK, Post>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                        \
+            attr_done = true;                                                                       \
+        }                                                                                           \
+        k_stencil_tma<F, OPK, Post><<<grid, kStencilThreads, smem, c->stream>>>(f, g, rc, post, fuse, tm); \
+    } else if (vec == 2)                                                                            \
+        k_stencil<F, OPK, 2, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);  \
+    else                                                                                            \
         k_stencil<F, OPK, 1, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);
     switch (op->kind) {
         case KL_OP_POISSON5: KL_ST_LAUNCH(KL_OP_POISSON5) break;

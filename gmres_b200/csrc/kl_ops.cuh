@@ -82,27 +82,18 @@ struct FChebStep : StencilBase<1, (MODE ? 1 : 0)> {
     double *d, *z_new;
     double theta, c1, c2;
     int first;
-    __device__ __forceinline__ void init() {}
+    FastDiv fd;
+    __device__ __forceinline__ void init() { fd.set(theta); }
+    __device__ __forceinline__ double point(const double (&v)[1]) const { return first ? fd.div(v[0]) : v[0]; }
     template <int VEC>
-    __device__ __forceinline__ void eval(const double *const (&rp)[1], int i, double (&u)[VEC]) const {
-        if (VEC == 2) {
-            double2 a = ldg2(rp[0] + i);
-            u[0] = first ? a.x / theta : a.x;
-            u[VEC - 1] = first ? a.y / theta : a.y;
-        } else {
-            double a = __ldg(rp[0] + i);
-            u[0] = first ? a / theta : a;
-        }
-    }
-    template <int VEC>
-    __device__ __forceinline__ void store(size_t idx, const double (&cu)[VEC], const double (&au)[VEC],
-                                          double *acc) const {
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[1][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
         double rr[VEC], dd[VEC], zz[VEC];
-        KL_LD(VEC, rr, r, idx)
         if (first) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) dd[v] = cu[v];
+            for (int v = 0; v < VEC; ++v) { rr[v] = raw[0][v]; dd[v] = cu[v]; }
         } else {
+            KL_LD(VEC, rr, r, idx)
             if (VEC == 2) {
                 double2 t = *reinterpret_cast<const double2 *>(d + idx);
                 dd[0] = t.x; dd[VEC - 1] = t.y;

@@ -300,3 +300,23 @@ def test_user_operator_callback(kl, h, ko):
     assert g.status == 0 and g.iter == r.iter
     assert np.allclose(g.x, r.x, rtol=0, atol=1e-12)
     h2.close()
+
+
+def test_fast_division_is_ieee_exact(kl, h, ko):
+    """The kernels divide by a kernel-constant with a hoisted reciprocal + two Markstein
+    corrections (kl_internal.cuh FastDiv); it must round exactly like the reference's r(i)/d."""
+    ns = 256
+    rng = np.random.default_rng(7)
+    mant = rng.uniform(1.0, 2.0, ns * ns) * rng.choice([-1.0, 1.0], ns * ns)
+    expo = rng.integers(-1000, 1000, ns * ns)
+    r = np.ldexp(mant, expo)
+    r[::7] = 0.0
+    r[3::11] = -0.0
+    r[5::13] = np.ldexp(mant[5::13], -1060)       # denormal quotients
+    r[1::17] = np.nextafter(8.4, 9.0) * rng.integers(1, 1 << 20, r[1::17].size)   # near-tie candidates
+    with np.errstate(all="ignore"):
+        for prm in (P, (1.0, 3.0), (0.3, 1.7), (7.9, 0.0001)):
+            z = h.apply_precond(kl.cbpr2, kl.stvec, r, prm, ns, ns)
+            zo = ko.apply_precond(ko.cbpr2_fn(), ko.stvec_fn(), r, prm, ns)
+            ok = (z == zo) | (np.isnan(z) & np.isnan(zo))
+            assert ok.all(), (prm, np.flatnonzero(~ok)[:5], z[~ok][:5], zo[~ok][:5])
