@@ -366,16 +366,18 @@ int kl_comm_rank(kl_handle_t h, int *rank, int *nranks) {
     return KL_OK;
 }
 
-int kl_partition(kl_handle_t h, int ny, int *j0, int *ny_local) {
-    if (!h || ny < 1) return KL_ERR_INVALID;
-    // contiguous lines, the first (ny % P) ranks get one extra line
-    const int P = h->nranks, p = h->rank;
-    const int base = ny / P, rem = ny % P;
-    const int start = p * base + (p < rem ? p : rem);
-    const int cnt = base + (p < rem ? 1 : 0);
-    if (j0) *j0 = start;
-    if (ny_local) *ny_local = cnt;
+int kl_partition_rank(int ny, int rank, int nranks, int *j0, int *ny_local) {
+    if (ny < 1 || nranks < 1 || rank < 0 || rank >= nranks) return KL_ERR_INVALID;
+    // contiguous lines in memory order, the first (ny % P) ranks get one extra line
+    const int base = ny / nranks, rem = ny % nranks;
+    if (j0) *j0 = rank * base + (rank < rem ? rank : rem);
+    if (ny_local) *ny_local = base + (rank < rem ? 1 : 0);
     return KL_OK;
+}
+
+int kl_partition(kl_handle_t h, int ny, int *j0, int *ny_local) {
+    if (!h) return KL_ERR_INVALID;
+    return kl_partition_rank(ny, h->rank, h->nranks, j0, ny_local);
 }
 
 // ---- device vectors -------------------------------------------------------

@@ -132,6 +132,8 @@ int kl_comm_init(kl_handle_t h, int rank, int nranks, const void *id /* same byt
 int kl_comm_rank(kl_handle_t h, int *rank, int *nranks);
 /* lines [j0, j0+ny_local) of a global nx*ny grid owned by this handle's rank */
 int kl_partition(kl_handle_t h, int ny, int *j0, int *ny_local);
+/* the same rule without a handle: contiguous lines, the first ny % nranks ranks get one more */
+int kl_partition_rank(int ny, int rank, int nranks, int *j0, int *ny_local);
 
 /* ---- device vectors (so that b/x can stay resident between calls) -------- */
 int kl_vec_alloc(kl_handle_t h, size_t n, double **d_ptr);
