@@ -231,7 +231,10 @@ def gpu_arm(args):
             del b
             torch.cuda.empty_cache()
             bn = bh.numpy()
+            xh = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+            run_gpu_solver(kl, h, w, bn, nx, ny, min(steps_eff, max(m, 3)))   # warm the host-buffer path
             barrier()
+            h.set_output_buffer(xh.numpy())
             t0 = time.perf_counter()
             r2 = run_gpu_solver(kl, h, w, bn, nx, ny, steps_eff)
             barrier()

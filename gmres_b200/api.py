@@ -308,7 +308,18 @@ class Handle:
         self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_HOST))
         return arr, C.c_void_p(arr.ctypes.data), False
 
+    def set_output_buffer(self, buf):
+        """Use `buf` (numpy array, e.g. a view of pinned memory, or CUDA tensor) for the next
+        solver call's x instead of allocating one (the reference's x is allocatable,intent(out))."""
+        self._xbuf = buf
+
     def _out_like(self, a, is_dev):
+        buf = getattr(self, "_xbuf", None)
+        if buf is not None:
+            self._xbuf = None
+            if is_dev:
+                return buf, C.c_void_p(buf.data_ptr())
+            return buf, C.c_void_p(buf.ctypes.data)
         if is_dev:
             import torch
             o = torch.empty_like(a)

@@ -60,6 +60,38 @@ int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
     return KL_OK;
 }
 
+static inline int ts_rm_host(int nc) { return nc <= 12 ? 8 : (nc <= 24 ? 4 : (nc <= 48 ? 2 : 1)); }
+int tmap_encode_v(Ctx *c, CUtensorMap *out, const double *V, size_t n, size_t ldv, int ncols_total, int nc) {
+    // key: (V, n, nc) -- ny field carries -nc so that it cannot collide with a grid map
+    for (auto &e : c->tmaps)
+        if (e.base == V && e.nx == (int)n && e.ny == -nc && e.k1 == (long long)ldv && e.k2 == ncols_total) {
+            memcpy(out, e.blob, sizeof(CUtensorMap));
+            return KL_OK;
+        }
+    if (!c->encode_fn) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled entry point", e);
+        c->encode_fn = fn;
+    }
+    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
+    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)ncols_total};
+    cuuint64_t strides[1] = {(cuuint64_t)ldv * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)(32 * ts_rm_host(nc)), (cuuint32_t)nc};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(V), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled (V) failed");
+    if (c->tmaps.size() >= 256) c->tmaps.clear();
+    Ctx::TmapEntry e;
+    e.base = V; e.nx = (int)n; e.ny = -nc; e.k1 = (long long)ldv; e.k2 = ncols_total;
+    memcpy(e.blob, out, sizeof(CUtensorMap));
+    c->tmaps.push_back(e);
+    return KL_OK;
+}
+
 void prof_reset(Ctx *c) {
     for (auto &r : c->prof_recs) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
     c->prof_recs.clear();

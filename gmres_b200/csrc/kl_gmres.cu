@@ -25,6 +25,7 @@
 #include <algorithm>
 
 #include "kl_gmres.cuh"
+#include "kl_tallskinny_tma.cuh"
 
 namespace kl {
 
@@ -35,11 +36,11 @@ __global__ void k_givens(const GmresDev G, const int j) {
 }
 
 // H(0..ncols-1, j) (+)= hvec   (gmres_mgsr.f90:351-353)
-__global__ void k_hacc(const GmresDev G, const int j, const int ncols, const int accumulate) {
+__global__ void k_hacc(const GmresDev G, const double *hv, const int j, const int ncols, const int accumulate) {
     if (G.I[I_CONV_AT] >= 0) return;
     double *Hj = G.H + (size_t)j * G.ldh;
     for (int c = threadIdx.x; c < ncols; c += blockDim.x)
-        Hj[c] = accumulate ? Hj[c] + G.hvec[c] : G.hvec[c];
+        Hj[c] = accumulate ? Hj[c] + hv[c] : hv[c];
 }
 
 // ---- tall-skinny projection  out[c] = V(:,c) . w , c < ncols ------------------
@@ -334,7 +335,45 @@ int launch_vtw(Ctx *c, const double *V, size_t ldv, const double *w, size_t n, i
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, out, ncols));
         if (h_mode) {
-            k_hacc<<<1, 128, 0, c->stream>>>(G, j, ncols, h_mode == 2);
+            k_hacc<<<1, 128, 0, c->stream>>>(G, out, j, ncols, h_mode == 2);
+            c->stats.kernel_launches++;
+        }
+    }
+    return KL_OK;
+}
+
+bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc) {
+    return c->opt_tma && nc >= 1 && nc <= kTsWarps * kTsCpw && n % 2 == 0 && ldv % 2 == 0 && n >= 4096 &&
+           n < (size_t)1 << 31;
+}
+
+int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
+                  const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated) {
+    CUtensorMap tm;
+    KL_TRY(tmap_encode_v(c, &tm, V, n, ldv, ncols_total, nc));
+    const size_t smem = ts_tma_smem(nc);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_ts_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_ts_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        attr_done = true;
+    }
+    const int RM = ts_rm(nc);
+    size_t ntiles = (n + (size_t)kTsRB * RM - 1) / ((size_t)kTsRB * RM);
+    int grid = (int)std::min<size_t>(ntiles, (size_t)kNumSM * 2);
+    const int hm = c->nranks == 1 ? h_mode : 0;
+    const int *fl = gated ? c->d_I : nullptr;
+    if (update)
+        k_ts_tma<true><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
+                                                              out, G, j, hm, fl);
+    else
+        k_ts_tma<false><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
+                                                               out, G, j, hm, fl);
+    c->stats.kernel_launches++;
+    if (c->nranks > 1) {
+        KL_TRY(comm_allreduce(c, out, nc));
+        if (h_mode) {
+            k_hacc<<<1, 128, 0, c->stream>>>(G, out, j, nc, h_mode == 2);
             c->stats.kernel_launches++;
         }
     }
@@ -405,7 +444,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
     size_t need = ws_need(ldv * (size_t)(m + 1)) + 6 * ws_need(n) + ws_need((size_t)ldh * m) +
-                  8 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
+                  10 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
     KL_TRY(ws_reserve(c, need));
     ws_reset(c);
     double *V = ws_take<double>(c, ldv * (size_t)(m + 1));
@@ -421,6 +460,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
     G.y = ws_take<double>(c, m + 2);
     G.fe = ws_take<double>(c, m + 2);
     G.hvec = ws_take<double>(c, m + 2);
+    G.hvec2 = ws_take<double>(c, m + 2);
     double *d_gram = ws_take<double>(c, (size_t)(m + 2) * (m + 2));
     G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
     G.m = m; G.ldh = ldh; G.mf = mf;
@@ -516,6 +556,16 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
                 }
                 bytes += (32.0 * total + 24.0) * n;
             } else {
+                if (ts_tma_ok(c, n, ldv, ncols)) {
+                    // 3 passes over V: project ; update + project (fused, V tile staged once) ; update + norm
+                    { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
+                      KL_TRY(launch_ts_tma(c, false, V, ldv, m + 1, wj, n, ncols, nullptr, G.hvec, G, j, 1, true)); }
+                    { ProfScope ps(c, 4, "gmres_wmvh_vtw_tma (w-=V h1 fused with h2=V^T w)", (8.0 * ncols + 16.0) * n);
+                      KL_TRY(launch_ts_tma(c, true, V, ldv, m + 1, wj, n, ncols, G.hvec, G.hvec2, G, j, 2, true)); }
+                    { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
+                      KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec2, true, G, j, true, true)); }
+                    bytes += (24.0 * ncols + 40.0) * n;
+                } else {
                 { ProfScope ps(c, 2, "gmres_vtw (h=V^T w tall-skinny projection)", (8.0 * ncols + 8.0) * n);
                   KL_TRY(launch_vtw(c, V, ldv, wj, n, ncols, G.hvec, G, j, 1, true)); }
                 { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
@@ -525,6 +575,7 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
                 { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
                   KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec, true, G, j, true, true)); }
                 bytes += (32.0 * ncols + 48.0) * n;
+                }
             }
             bytes += (24.0 + (prec ? 16.0 : 0.0)) * n;
             norm_idx = S_HVAL;

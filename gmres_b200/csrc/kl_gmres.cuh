@@ -14,7 +14,7 @@ constexpr int kTsMaxBlocks = 1024;  // partials leading dimension
 
 struct GmresDev {
     double *H;      // (m+1) x m, ldh = m+1
-    double *g, *cs, *sn, *y, *fe, *hvec;
+    double *g, *cs, *sn, *y, *fe, *hvec, *hvec2;
     double *S;
     int *I;
     double *hist;
@@ -127,6 +127,10 @@ struct PostMgs {
 int launch_vtw(Ctx *c, const double *V, size_t ldv, const double *w, size_t n, int ncols, double *out,
                const GmresDev &G, int j, int h_mode, bool gated);
 int launch_backsolve(Ctx *c, const GmresDev &G);
+// TMA-staged projection (update = false) or update + second projection (update = true)
+bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc);
+int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
+                  const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated);
 int gram_lower(Ctx *c, const double *V, size_t ldv, size_t n, int k, double *d_gram, std::vector<double> &out);
 
 }  // namespace kl

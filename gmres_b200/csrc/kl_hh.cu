@@ -253,6 +253,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     G.y = ws_take<double>(c, m + 2);
     G.fe = ws_take<double>(c, m + 2);
     G.hvec = ws_take<double>(c, m + 2);
+    G.hvec2 = G.hvec;
     double *d_gram = ws_take<double>(c, (size_t)(m + 2) * (m + 2));
     G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
     G.m = m; G.ldh = ldh; G.mf = 0;

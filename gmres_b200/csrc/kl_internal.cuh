@@ -112,7 +112,7 @@ struct kl_context_s {
     int history_len = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // TMA descriptor cache (opaque 128-byte CUtensorMap blobs keyed by base pointer and extents)
-    struct TmapEntry { const void *base; int nx, ny; alignas(64) unsigned char blob[128]; };
+    struct TmapEntry { const void *base; int nx, ny; long long k1 = 0, k2 = 0; alignas(64) unsigned char blob[128]; };
     std::vector<TmapEntry> tmaps;
     void *encode_fn = nullptr;
     // profiling (KL_OPT_PROFILE): event pairs per kernel class, resolved after the solve

@@ -1,0 +1,165 @@
+// kl_tallskinny_tma.cuh -- TMA-staged tall-skinny kernels for the Gram-Schmidt passes.
+//
+//   UPDATE = false :  h_out = V(:,0..nc-1)^T w                        (projection)
+//   UPDATE = true  :  w <- w - V h_in ; h_out = V^T w (the NEW w)     (update fused with the
+//                     second projection: the V tile is read from HBM once for both)
+//
+// A CTA streams row tiles of V (kTsRB = 32 rows x nc columns, one 2-D TMA box per tile,
+// [col][row] in shared memory) through a kTsNst-deep mbarrier ring.  Thread layout:
+// lane = row inside the tile, warp = column slice (kTsCpw columns).  Each thread loads its
+// slice of the tile row into registers once and uses it for both the update (reduction
+// across warps through shared memory) and the projection (per-thread accumulators, reduced
+// across lanes only once at the end of the kernel).  Deterministic two-stage reduction as
+// in k_vtw.  Requires nc <= 8*kTsCpw = 96 columns, n and ldv even.
+#pragma once
+#include "kl_stencil_tma.cuh"
+
+namespace kl {
+
+constexpr int kTsRB = 32;    // rows per warp-row-group; a tile has kTsRB * RM rows (RM = 1,2,4,8)
+constexpr int kTsNst = 4;    // ring depth
+// row-group multiplier: few columns -> taller tiles, so that a tile stays ~16-24 KB and the
+// eight warps split into RM row groups x 8/RM column slices
+inline int ts_rm(int nc) { return nc <= 12 ? 8 : (nc <= 24 ? 4 : (nc <= 48 ? 2 : 1)); }
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kTsThreads, 2)
+k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, const int nc, const int RM,
+         const double *__restrict__ h_in, double *__restrict__ partials, unsigned int *counter,
+         double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
+         const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int RB = kTsRB * RM;                                  // rows per tile
+    const int nslice = kTsWarps / RM;                            // column slices
+    const int rowgrp = wid % RM, slice = wid / RM;
+    const unsigned tile_doubles = (unsigned)RB * nc;
+    const unsigned tile_bytes = tile_doubles * sizeof(double);
+    const unsigned tile_stride = (tile_bytes + 127u) & ~127u;
+    double *tiles = reinterpret_cast<double *>(smem_raw);
+    unsigned char *p = smem_raw + (size_t)kTsNst * tile_stride;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(p);
+    p += 64;
+    double *s_h = reinterpret_cast<double *>(p);               // nc (padded to 96)
+    p += 96 * sizeof(double);
+    double *s_part = reinterpret_cast<double *>(p);            // [slice][RB rows] = 256 doubles
+    p += 8 * kTsRB * sizeof(double);
+    double *s_red = reinterpret_cast<double *>(p);             // [rowgrp * 8 + slice][kTsCpw]
+    __shared__ int s_last;
+
+    const size_t ntiles = (n + RB - 1) / RB;
+    const int c0 = slice * kTsCpw;                             // first column of this warp's slice
+    int ncw = nc - c0;                                         // columns in this slice
+    ncw = ncw < 0 ? 0 : (ncw > kTsCpw ? kTsCpw : ncw);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTsNst; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (UPDATE)
+        for (int c = threadIdx.x; c < nc; c += kTsThreads) s_h[c] = h_in[c];
+    __syncthreads();
+    auto issue = [&](size_t t, int s) {
+        mbar_expect_tx(&full[s], tile_bytes);
+        tma_load_2d(reinterpret_cast<unsigned char *>(tiles) + (size_t)s * tile_stride, &tmV, &full[s],
+                    (int)(t * RB), 0);
+    };
+    // tiles of this CTA: t = blockIdx.x + k * gridDim.x
+    size_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (size_t k = 0; k < (size_t)kTsNst && k < my_tiles; ++k) issue(blockIdx.x + k * gridDim.x, (int)k);
+    }
+    double acc[kTsCpw];
+#pragma unroll
+    for (int c = 0; c < kTsCpw; ++c) acc[c] = 0.0;
+    // w of the first tile (register prefetch, one tile ahead)
+    const int rin = rowgrp * kTsRB + lane;                     // row inside the tile
+    size_t row = (size_t)blockIdx.x * RB + rin;
+    double wnext = (my_tiles > 0 && row < n) ? w[row] : 0.0;
+
+    for (size_t k = 0; k < my_tiles; ++k) {
+        const int s = (int)(k % kTsNst);
+        const size_t t = blockIdx.x + k * gridDim.x;
+        row = t * RB + rin;
+        double wr = wnext;
+        {
+            const size_t rn = (t + gridDim.x) * RB + rin;
+            wnext = (k + 1 < my_tiles && rn < n) ? w[rn] : 0.0;
+        }
+        mbar_wait(&full[s], (unsigned)((k / kTsNst) & 1));
+        const double *tile = reinterpret_cast<const double *>(reinterpret_cast<unsigned char *>(tiles) +
+                                                               (size_t)s * tile_stride);
+        double v[kTsCpw];
+#pragma unroll
+        for (int c = 0; c < kTsCpw; ++c) v[c] = (c < ncw) ? tile[(size_t)(c0 + c) * RB + rin] : 0.0;
+        if (UPDATE) {
+            double part = 0.0;
+#pragma unroll
+            for (int c = 0; c < kTsCpw; ++c)
+                if (c < ncw) part = fma(s_h[c0 + c], v[c], part);
+            s_part[slice * RB + rin] = part;
+            __syncthreads();
+            double sum = 0.0;
+            for (int q = 0; q < nslice; ++q) sum += s_part[q * RB + rin];
+            wr = wr - sum;
+            if (slice == 0 && row < n) w[row] = wr;
+        }
+#pragma unroll
+        for (int c = 0; c < kTsCpw; ++c) acc[c] = fma(v[c], wr, acc[c]);
+        __syncthreads();   // tile s (and s_part) consumed by every thread
+        if (threadIdx.x == 0 && k + kTsNst < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(blockIdx.x + (k + kTsNst) * gridDim.x, s);
+        }
+    }
+    // ---- block stage: reduce over the 32 row-lanes, then over the RM row groups
+#pragma unroll
+    for (int c = 0; c < kTsCpw; ++c) {
+        double sv = warp_sum(acc[c]);
+        if (lane == 0) s_red[(rowgrp * 8 + slice) * kTsCpw + c] = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x < nc) {
+        const int sl = threadIdx.x / kTsCpw, cc = threadIdx.x % kTsCpw;
+        double sv = 0.0;
+        for (int q = 0; q < RM; ++q) sv += s_red[(q * 8 + sl) * kTsCpw + cc];
+        partials[(size_t)threadIdx.x * kTsMaxBlocks + blockIdx.x] = sv;
+    }
+    // ---- grid stage (same as k_vtw)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned prev = atomicAdd(counter, 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int col = wid; col < nc; col += kTsWarps) {
+        const volatile double *pp = partials + (size_t)col * kTsMaxBlocks;
+        double sv = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) sv += pp[b];
+        sv = warp_sum(sv);
+        if (lane == 0) {
+            out[col] = sv;
+            if (h_mode) {
+                double *Hj = G.H + (size_t)j * G.ldh;
+                Hj[col] = (h_mode == 2) ? Hj[col] + sv : sv;
+            }
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+inline size_t ts_tma_smem(int nc) {
+    const size_t tile_stride = ((size_t)kTsRB * ts_rm(nc) * nc * sizeof(double) + 127) & ~size_t(127);
+    return kTsNst * tile_stride + 64 + 96 * sizeof(double) + 8 * kTsRB * sizeof(double) +
+           64 * kTsCpw * sizeof(double) + 128;
+}
+
+// host: 2-D FP64 tensor map over V (n rows fastest, ncols columns, ld = ldv), box kTsRB x nc
+int tmap_encode_v(Ctx *c, CUtensorMap *out, const double *V, size_t n, size_t ldv, int ncols_total, int nc);
+
+}  // namespace kl
