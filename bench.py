@@ -220,9 +220,21 @@ def gpu_arm(args):
             out["kernels"] = prof
             dom = max(prof, key=lambda p: p["ms"]) if prof else None
             if dom:
+                traffic, tsrc = None, None
+                try:
+                    with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as tf:
+                        tj = json.load(tf)
+                    key = dom["name"].split(" ")[0]
+                    ent = tj["bytes_per_unknown"].get(key)
+                    if ent and "measured" in ent:
+                        traffic = ent["measured"] * n_loc      # bytes per launch on this rank
+                        tsrc = tj["source"]
+                except Exception:
+                    pass
                 out["roofline"] = dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s",
-                                       frac=dom["gbs"] / peak, traffic=None, kernel=dom["name"],
-                                       avg_launch_us=dom["avg_us"], peak_source=which)
+                                       frac=dom["gbs"] / peak, traffic=traffic, kernel=dom["name"],
+                                       algorithmic_bytes_per_launch=dom["algorithmic_bytes"] / dom["launches"],
+                                       avg_launch_us=dom["avg_us"], peak_source=which, traffic_source=tsrc)
             h.set_option(8, 0)
         if with_e2e:
             # the reference-facing call with HOST buffers: H2D of b and D2H of x inside the timed region
