@@ -348,7 +348,8 @@ bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc) {
 }
 
 int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
-                  const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated) {
+                  const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated,
+                  long long tail0) {
     CUtensorMap tm;
     KL_TRY(tmap_encode_v(c, &tm, V, n, ldv, ncols_total, nc));
     const size_t smem = ts_tma_smem(nc);
@@ -365,13 +366,13 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     const int *fl = gated ? c->d_I : nullptr;
     if (update)
         k_ts_tma<true><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                              out, G, j, hm, fl);
+                                                              out, G, j, hm, fl, tail0);
     else
         k_ts_tma<false><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                               out, G, j, hm, fl);
+                                                               out, G, j, hm, fl, tail0);
     c->stats.kernel_launches++;
     if (c->nranks > 1) {
-        KL_TRY(comm_allreduce(c, out, nc));
+        KL_TRY(comm_allreduce(c, out, nc + (tail0 >= 0 ? 1 : 0)));
         if (h_mode) {
             k_hacc<<<1, 128, 0, c->stream>>>(G, out, j, nc, h_mode == 2);
             c->stats.kernel_launches++;

@@ -186,6 +186,214 @@ __global__ void k_hh_first(const GmresDev G, const double *w) {
     G.S[S_NORM] = sqrt(fma(pv, pv, S2));                     // :253 norm2(w)
 }
 
+
+// ===========================================================================
+// KL_HH_BLOCKED: compact-WY form.  Q_j = P_0 ... P_j = I - Y T Y^T with Y = [p_0 .. p_j],
+// T upper triangular, T(:,j+1) = -2 T (Y^T p_{j+1}), T(j+1,j+1) = 2.  Per Arnoldi step the
+// reflector products become three tall-skinny passes over Y (24 n j bytes instead of 64 n j):
+//   v_j = e_j - Y (T Y(j,:)^T)                       k_hh_apply_wy (src = e_j)
+//   s   = Y^T w                                      k_ts_tma<false>
+//   w  -= Y (T^T s) ; u = Y^T w ; tail ||w||^2       k_ts_tma<true>
+// and the O(j^2) triangular products run on one warp.  Ytop holds the first m+1 rows of Y
+// (reflector i is zero above row i), which is all the scalar part ever needs.
+// ===========================================================================
+struct HhWy {
+    double *T;      // (m+1) x (m+1) column-major, ldt = m+1
+    double *Ytop;   // (m+2) x (m+1) column-major, ldy = m+2
+    double *tvec, *svec;
+    int ldt, ldy;
+};
+
+// tvec(0..j) = T(0..j,0..j) * Ytop(row, 0..j)      (row = j: v_j ; also used by calculate_verr)
+__global__ void k_wy_pre(const GmresDev G, const HhWy W, const int j, const int gated) {
+    if (gated && G.I[I_CONV_AT] >= 0) return;
+    for (int r = threadIdx.x; r <= j; r += 32) {
+        double t = 0.0;
+        for (int c = r; c <= j; ++c) t = fma(W.T[(size_t)c * W.ldt + r], W.Ytop[(size_t)c * W.ldy + j], t);
+        W.tvec[r] = t;
+    }
+}
+// tvec(0..j) = T(0..j,0..j)^T * svec(0..j)
+__global__ void k_wy_tT(const GmresDev G, const HhWy W, const int j) {
+    if (G.I[I_CONV_AT] >= 0) return;
+    for (int c = threadIdx.x; c <= j; c += 32) {
+        double t = 0.0;
+        for (int r = 0; r <= c; ++r) t = fma(W.T[(size_t)c * W.ldt + r], W.svec[r], t);
+        W.tvec[c] = t;
+    }
+}
+// cycle end: svec = Ytop(0..k-1, 0..k-1)^T y ; tvec = T_k svec    (x += [y;0] - Y tvec)
+__global__ void k_wy_xs(const GmresDev G, const HhWy W, const int k) {
+    extern __shared__ double sm[];
+    for (int c = threadIdx.x; c < k; c += 32) {
+        double t = 0.0;
+        for (int r = c; r < k; ++r) t = fma(W.Ytop[(size_t)c * W.ldy + r], G.y[r], t);
+        sm[c] = t;
+    }
+    __syncwarp();
+    for (int r = threadIdx.x; r < k; r += 32) {
+        double t = 0.0;
+        for (int c = r; c < k; ++c) t = fma(W.T[(size_t)c * W.ldt + r], sm[c], t);
+        W.tvec[r] = t;
+    }
+}
+
+// out = src - Y(:,0..nc-1) t ; src = e_row (mode 1) or [y(0..row-1); 0] (mode 2) ; dst: store or x += .
+template <int VEC>
+__global__ void __launch_bounds__(kTsThreads)
+k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, const double *__restrict__ t,
+              const int src_mode, const long long row, const double *__restrict__ yv, double *dst,
+              const int add_to_dst, const size_t n, const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    extern __shared__ double sh[];
+    for (int c = threadIdx.x; c < nc; c += kTsThreads) sh[c] = t[c];
+    __syncthreads();
+    const size_t nchunk = n / VEC;
+    for (size_t ch = (size_t)blockIdx.x * kTsThreads + threadIdx.x; ch < nchunk;
+         ch += (size_t)gridDim.x * kTsThreads) {
+        const size_t r = ch * VEC;
+        double a[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const long long rr = (long long)(r + e);
+            a[e] = src_mode == 1 ? (rr == row ? 1.0 : 0.0) : (rr < row ? yv[rr] : 0.0);
+        }
+        int c = 0;
+        for (; c + 8 <= nc; c += 8) {
+            double v[8][VEC];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double *col = Y + (size_t)(c + q) * ldv + r;
+                if (VEC == 2) {
+                    double2 tt = ldg2(col);
+                    v[q][0] = tt.x; v[q][VEC - 1] = tt.y;
+                } else {
+                    v[q][0] = __ldg(col);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double hq = -sh[c + q];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) a[e] = fma(hq, v[q][e], a[e]);
+            }
+        }
+        for (; c < nc; ++c) {
+            const double *col = Y + (size_t)c * ldv + r;
+            const double hq = -sh[c];
+            if (VEC == 2) {
+                double2 tt = ldg2(col);
+                a[0] = fma(hq, tt.x, a[0]);
+                a[VEC - 1] = fma(hq, tt.y, a[VEC - 1]);
+            } else {
+                a[0] = fma(hq, __ldg(col), a[0]);
+            }
+        }
+        if (add_to_dst) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a[e] = dst[r + e] + a[e];
+        }
+        if (VEC == 2) stg2(dst + r, a[0], a[VEC - 1]);
+        else dst[r] = a[0];
+    }
+}
+
+// first reflector of a cycle in WY form: k_hh_first + T(0,0) = 2 + Ytop(:,0)
+__global__ void k_hh_first_wy(const GmresDev G, const HhWy W, const double *w) {
+    const int lane = threadIdx.x;
+    double pv = 0.0, nw = 1.0;
+    if (lane == 0) {
+        const double ss = G.S[S_RED];
+        const double w0 = w[0];
+        const double beta = sqrt(ss);
+        const double sg = copysign(beta, w0);
+        G.g[0] = -sg;
+        pv = sg + w0;
+        double S2 = ss - w0 * w0;
+        if (S2 < 0.0) S2 = 0.0;
+        nw = sqrt(fma(pv, pv, S2));
+        G.S[S_TMP1] = pv;
+        G.S[S_NORM] = nw;
+        W.T[0] = 2.0;
+    }
+    pv = __shfl_sync(0xffffffffu, pv, 0);
+    nw = __shfl_sync(0xffffffffu, nw, 0);
+    for (int r = lane; r <= G.m; r += 32) W.Ytop[r] = (r == 0 ? pv : w[r]) / nw;
+}
+
+// serial block of the reference in WY form by ONE WARP: H(:,j), Householder pivot, new column of
+// Ytop and of T, Givens update (gmres_hh.f90:305-345).  u = Y^T w (u[0..j]) and the tail sum u[j+1].
+__global__ void k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, const int j,
+                             const int prec_variant) {
+    extern __shared__ double sm[];     // 3*(m+2) for Givens + (m+2) for z
+    if (G.I[I_CONV_AT] >= 0) return;
+    const int lane = threadIdx.x;
+    double *sh = sm, *sz = sm + 3 * (G.m + 2);
+    double *Hj = G.H + (size_t)j * G.ldh;
+    for (int i = lane; i <= j; i += 32) {          // :306 H(1:j,j) = w(1:j)
+        const double t = w[i];
+        sh[i] = t;
+        Hj[i] = t;
+    }
+    double hj1 = 0.0, pv = 0.0, nw = 1.0;
+    if (lane == 0) {
+        const double S2 = u[j + 1];
+        const double piv = w[j + 1];
+        const double tmp = sqrt(fma(piv, piv, S2));
+        hj1 = (piv > 0.0) ? -tmp : tmp;
+        pv = piv - hj1;
+        nw = sqrt(fma(pv, pv, S2));
+        G.S[S_TMP1] = pv;
+        G.S[S_NORM] = nw;
+    }
+    hj1 = __shfl_sync(0xffffffffu, hj1, 0);
+    pv = __shfl_sync(0xffffffffu, pv, 0);
+    nw = __shfl_sync(0xffffffffu, nw, 0);
+    __syncwarp();
+    if (j + 1 <= G.m) {
+        // Ytop(:, j+1) = masked w / nw
+        for (int r = lane; r <= G.m; r += 32)
+            W.Ytop[(size_t)(j + 1) * W.ldy + r] = r <= j ? 0.0 : ((r == j + 1 ? pv : w[r]) / nw);
+        // z = Y^T p_{j+1} = (u - sum_{r<=j} Ytop(r,:) w_r - Ytop(j+1,:) hj1) / nw
+        for (int c = lane; c <= j; c += 32) {
+            double t = u[c];
+            for (int r = c; r <= j; ++r) t = fma(-W.Ytop[(size_t)c * W.ldy + r], sh[r], t);
+            t = fma(-W.Ytop[(size_t)c * W.ldy + j + 1], hj1, t);
+            sz[c] = t / nw;
+        }
+        __syncwarp();
+        // T(0..j, j+1) = -2 T z ; T(j+1,j+1) = 2
+        for (int r = lane; r <= j; r += 32) {
+            double t = 0.0;
+            for (int c = r; c <= j; ++c) t = fma(W.T[(size_t)c * W.ldt + r], sz[c], t);
+            W.T[(size_t)(j + 1) * W.ldt + r] = -2.0 * t;
+        }
+        if (lane == 0) W.T[(size_t)(j + 1) * W.ldt + j + 1] = 2.0;
+    }
+    __syncwarp();
+    const int conv_before = G.I[I_CONV_AT];
+    givens_update_warp(G, j, hj1, lane, sm, false);
+    if (lane == 0 && !prec_variant) {
+        if (G.I[I_BREAKDOWN] == 0) G.I[I_CONV_AT] = conv_before;
+    }
+}
+
+static int launch_apply_wy(Ctx *c, const double *Y, size_t ldv, int nc, const double *t, int src_mode, long long row,
+                           const double *yv, double *dst, int add, size_t n, bool gated) {
+    const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
+    size_t b = (n / vec + kTsThreads - 1) / kTsThreads;
+    if (b > (size_t)kNumSM * 8) b = (size_t)kNumSM * 8;
+    const size_t smem = sizeof(double) * (nc + 8);
+    if (vec == 2)
+        k_hh_apply_wy<2><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
+                                                                 gated ? c->d_I : nullptr);
+    else
+        k_hh_apply_wy<1><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
+                                                                 gated ? c->d_I : nullptr);
+    c->stats.kernel_launches++;
+    return KL_OK;
+}
+
 struct HhRun {
     Ctx *c;
     Prob *P;
@@ -236,7 +444,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
     size_t need = ws_need(ldv * (size_t)(m + 1)) + (c->opt_verr ? ws_need(ldv * (size_t)m) : 0) + 7 * ws_need(n) +
-                  ws_need((size_t)ldh * m) + 8 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
+                  ws_need((size_t)ldh * m) + 12 * ws_need(m + 2) + 3 * ws_need((size_t)(m + 2) * (m + 2));
     KL_TRY(ws_reserve(c, need));
     ws_reset(c);
     double *Pm = ws_take<double>(c, ldv * (size_t)(m + 1));
@@ -258,6 +466,17 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
     G.m = m; G.ldh = ldh; G.mf = 0;
     HhRun R{c, &P, G, Pm, ldv, n, 0.0};
+    const bool blocked = c->opt_hh_mode == KL_HH_BLOCKED && ts_tma_ok(c, n, ldv, m);
+    HhWy W;
+    W.ldt = m + 1; W.ldy = m + 2;
+    W.T = ws_take<double>(c, (size_t)(m + 1) * (m + 1));
+    W.Ytop = ws_take<double>(c, (size_t)(m + 2) * (m + 1));
+    W.tvec = ws_take<double>(c, m + 2);
+    W.svec = ws_take<double>(c, m + 2);
+    if (blocked) {
+        KL_CUDA(c, cudaMemsetAsync(W.T, 0, sizeof(double) * (size_t)(m + 1) * (m + 1), c->stream));
+        KL_CUDA(c, cudaMemsetAsync(W.Ytop, 0, sizeof(double) * (size_t)(m + 2) * (m + 1), c->stream));
+    }
 
     if (!dev) KL_TRY(stage_in(c, db, b, n));
     KL_CUDA(c, cudaMemsetAsync(dx, 0, n * sizeof(double), c->stream));
@@ -298,7 +517,8 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
             d.a = w; d.b = w; d.c = nullptr; d.d = nullptr;
             KL_TRY(launch_pointwise(c, d, n, NoPost{}));
         }
-        k_hh_first<<<1, 32, 0, c->stream>>>(G, w);           // :250-252
+        if (blocked) k_hh_first_wy<<<1, 32, 0, c->stream>>>(G, W, w);
+        else k_hh_first<<<1, 32, 0, c->stream>>>(G, w);           // :250-252
         {
             PHhNewReflector f;                                // :253 P(:,1) = w / norm2(w)
             set_gate(f, c, false);
@@ -308,6 +528,30 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
         c->stats.kernel_launches++;
         R.bytes += 56.0 * n;
         for (int j = 0; j < m; ++j) {
+            if (blocked) {
+                const int nc = j + 1;
+                // v_j = e_j - Y (T Ytop(j,:)^T)
+                k_wy_pre<<<1, 32, 0, c->stream>>>(G, W, j, 1);
+                KL_TRY(launch_apply_wy(c, Pm, ldv, nc, W.tvec, 1, j, nullptr, vj, 0, n, true));
+                if (prec) {
+                    KL_TRY(op_apply(&P, vj, z, true));
+                    KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
+                } else {
+                    KL_TRY(op_apply(&P, vj, w, true));
+                }
+                // s = Y^T w ; t = T^T s ; w -= Y t fused with u = Y^T w and the tail norm
+                KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true));
+                k_wy_tT<<<1, 32, 0, c->stream>>>(G, W, j);
+                KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
+                k_hh_step_wy<<<1, 32, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
+                c->stats.kernel_launches += 3;
+                PHhNewReflector f;
+                set_gate(f, c, true, j, 1);
+                f.w = w; f.p_out = Pm + (size_t)(j + 1) * ldv; f.S = c->d_S; f.piv = (long long)j + 1;
+                KL_TRY(launch_pointwise(c, f, n, NoPost{}));
+                R.bytes += (24.0 * nc + 32.0 + 16.0 + (prec ? 32.0 : 16.0)) * n;
+                continue;
+            }
             // v = P_0 ... P_j e_j  (:257-283): reflectors applied in the order j, j-1, ..., 0
             {
                 PHhInit f;
@@ -365,7 +609,12 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
         KL_TRY(read_back(c));
         n_out = c->h_pinned_i[I_NOUT];
         // w = [y;0] ; w = P_0 ... P_{n_out-1} w ; x += w  (:356-378)
-        {
+        if (blocked) {
+            k_wy_xs<<<1, 32, sizeof(double) * (m + 2), c->stream>>>(G, W, n_out);
+            c->stats.kernel_launches++;
+            KL_TRY(launch_apply_wy(c, Pm, ldv, n_out, W.tvec, 2, n_out, G.y, dx, 1, n, false));
+            R.bytes += (8.0 * n_out + 16.0) * n;
+        } else {
             PHhLoadY f;
             set_gate(f, c, false);
             f.w = w; f.y = G.y; f.pnext = Pm + (size_t)(n_out - 1) * ldv; f.n_out = n_out;
@@ -391,6 +640,11 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
         // calculate_verr (:568-593): V_i = P_0 ... P_i e_i, i < n_out
         for (int i = 0; i < n_out; ++i) {
             double *Vi = Vb + (size_t)i * ldv;
+            if (blocked) {
+                k_wy_pre<<<1, 32, 0, c->stream>>>(G, W, i, 0);
+                KL_TRY(launch_apply_wy(c, Pm, ldv, i + 1, W.tvec, 1, i, nullptr, Vi, 0, n, false));
+                continue;
+            }
             PHhInit f;
             set_gate(f, c, false);
             f.v = Vi; f.pj = Pm + (size_t)i * ldv; f.pnext = i > 0 ? Pm + (size_t)(i - 1) * ldv : nullptr;

@@ -83,7 +83,7 @@ struct kl_context_s {
     int opt_verr = 1;
     int opt_check_every = 32;
     int opt_use_graph = 1;
-    int opt_hh_mode = KL_HH_SEQUENTIAL;
+    int opt_hh_mode = KL_HH_BLOCKED;
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_tma = 1;

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kTsThreads, 2)
 k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, const int nc, const int RM,
          const double *__restrict__ h_in, double *__restrict__ partials, unsigned int *counter,
          double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
-         const int *__restrict__ flags) {
+         const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */) {
     if (flags && flags[I_CONV_AT] >= 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -74,6 +74,7 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
     double acc[kTsCpw];
 #pragma unroll
     for (int c = 0; c < kTsCpw; ++c) acc[c] = 0.0;
+    double nacc = 0.0;
     // w of the first tile (register prefetch, one tile ahead)
     const int rin = rowgrp * kTsRB + lane;                     // row inside the tile
     size_t row = (size_t)blockIdx.x * RB + rin;
@@ -108,6 +109,7 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
         }
 #pragma unroll
         for (int c = 0; c < kTsCpw; ++c) acc[c] = fma(v[c], wr, acc[c]);
+        if (tail0 >= 0 && slice == 0 && (long long)row >= tail0 && row < n) nacc = fma(wr, wr, nacc);
         __syncthreads();   // tile s (and s_part) consumed by every thread
         if (threadIdx.x == 0 && k + kTsNst < my_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -127,6 +129,17 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
         for (int q = 0; q < RM; ++q) sv += s_red[(q * 8 + sl) * kTsCpw + cc];
         partials[(size_t)threadIdx.x * kTsMaxBlocks + blockIdx.x] = sv;
     }
+    if (tail0 >= 0) {
+        __syncthreads();
+        double sv = warp_sum(nacc);
+        if (lane == 0) s_red[wid] = sv;     // only slice-0 warps hold non-zero values
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < kTsWarps; ++q) t += s_red[q];
+            partials[(size_t)nc * kTsMaxBlocks + blockIdx.x] = t;
+        }
+    }
     // ---- grid stage (same as k_vtw)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -137,14 +150,15 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int col = wid; col < nc; col += kTsWarps) {
+    const int ncr = nc + (tail0 >= 0 ? 1 : 0);
+    for (int col = wid; col < ncr; col += kTsWarps) {
         const volatile double *pp = partials + (size_t)col * kTsMaxBlocks;
         double sv = 0.0;
         for (unsigned b = lane; b < gridDim.x; b += 32) sv += pp[b];
         sv = warp_sum(sv);
         if (lane == 0) {
             out[col] = sv;
-            if (h_mode) {
+            if (h_mode && col < nc) {
                 double *Hj = G.H + (size_t)j * G.ldh;
                 Hj[col] = (h_mode == 2) ? Hj[col] + sv : sv;
             }

@@ -120,7 +120,7 @@ enum {
 };
 enum {
     KL_HH_SEQUENTIAL = 0, /* reflector by reflector, the reference's order (gmres_hh.f90:269-304) */
-    KL_HH_BLOCKED = 1     /* compact-WY, three tall-skinny passes per step                        */
+    KL_HH_BLOCKED = 1     /* compact-WY, three tall-skinny passes per step (default when n >= 4096, m <= 96) */
 };
 int kl_set_option(kl_handle_t h, int key, int value);
 int kl_get_option(kl_handle_t h, int key, int *value);

@@ -229,9 +229,14 @@ def test_bicgstab_unpreconditioned(kl, h, ko):
 
 @pytest.mark.parametrize("ns,m", [(100, 95), (300, 95), (100, 20)])
 def test_gmres_hh_prec_parity(kl, h, ko, ns, m):
+    """KL_HH_SEQUENTIAL: reflector by reflector, the reference's order."""
     b = ko.manufactured_rhs(ko.stvec_fn(), ns)
     o = ko.gmres_hh(ko.stvec_fn(), b, m, 1e-8, ko.cbpr2_fn(), P, want_orth=True)
-    g = h.gmres_hh_prec_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
+    h.set_option(6, 0)
+    try:
+        g = h.gmres_hh_prec_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
+    finally:
+        h.set_option(6, 1)
     gi, oi = _its(g, m), _its(o, m)
     k = min(g.history.size, o.history.size)
     rel = np.abs(g.history[:k] / o.history[:k] - 1)
@@ -320,3 +325,24 @@ def test_fast_division_is_ieee_exact(kl, h, ko):
             zo = ko.apply_precond(ko.cbpr2_fn(), ko.stvec_fn(), r, prm, ns)
             ok = (z == zo) | (np.isnan(z) & np.isnan(zo))
             assert ok.all(), (prm, np.flatnonzero(~ok)[:5], z[~ok][:5], zo[~ok][:5])
+
+
+@pytest.mark.parametrize("ns,m", [(100, 95), (300, 95), (128, 24)])
+def test_gmres_hh_blocked_compact_wy(kl, h, ko, ns, m):
+    """KL_HH_BLOCKED: the reflector products in compact-WY form (three tall-skinny passes per
+    step).  Same algorithm in exact arithmetic as gmres_hh.f90's sequential reflectors."""
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    o = ko.gmres_hh(ko.stvec_fn(), b, m, 1e-8, ko.cbpr2_fn(), P, want_orth=True)
+    h.set_option(6, 1)     # KL_OPT_HH_MODE = KL_HH_BLOCKED (the default)
+    g = h.gmres_hh_prec_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
+    g0 = h.gmres_hh_omp(kl.stvec, b, min(m, 30), 1e-8) if ns == 100 else None
+    gi, oi = _its(g, m), _its(o, m)
+    k = min(g.history.size, o.history.size)
+    rel = np.abs(g.history[:k] / o.history[:k] - 1)
+    print(f"hh_blocked ns={ns} m={m}: its gpu {gi} oracle {oi}; hist rel {rel.max():.2e}; x diff {np.abs(g.x - o.x).max():.2e}; "
+          f"v_err max {g.v_err.max():.2e}; frob {g.stats['orth_frobenius']:.2e}")
+    assert g.status == 0 and abs(gi - oi) <= 1
+    assert rel.max() < 1e-8 and np.abs(g.x - o.x).max() < 1e-9
+    assert g.v_err.max() < 1e-27 and g.stats["orth_frobenius"] < 1e-11
+    if g0 is not None:
+        assert g0.status == 0 and np.abs(g0.x - 1).max() < 1e-4
