@@ -2,6 +2,8 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -238,7 +240,7 @@ int kl_create(kl_handle_t *h, int device) {
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_S, sizeof(double) * S_COUNT) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_I, sizeof(int) * I_COUNT) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxCols * kMaxBlocks / 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_partials, sizeof(double) * std::max((size_t)kMaxCols * 1024, (size_t)kMaxRed * kMaxBlocks)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_counter, sizeof(unsigned) * 16) == cudaSuccess;
     c->hist_cap = 1 << 20;
     ok = ok && cudaMalloc(&c->d_hist, sizeof(double) * c->hist_cap) == cudaSuccess;

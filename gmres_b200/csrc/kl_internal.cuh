@@ -29,7 +29,7 @@ namespace kl {
 // limits
 // ------------------------------------------------------------------------
 constexpr int kMaxRed = 8;          // reductions per point-wise / stencil kernel
-constexpr int kMaxBlocks = 4096;    // upper bound on reducing-kernel grid size
+constexpr int kMaxBlocks = 8192;    // upper bound on reducing-kernel grid size (partials leading dimension)
 constexpr int kMaxCols = 512;       // max restart length m+1 supported by the tall-skinny kernels
 constexpr int kNumSM = 148;
 
@@ -574,7 +574,10 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     Geo g{nx, ny, stencil_rows(nx, ny, vec)};
     dim3 grid((nx + strip - 1) / strip, (ny + g.rows - 1) / g.rows);
     if ((long)grid.x * grid.y > kMaxBlocks) {
-        g.rows = (int)(((long)ny * grid.x + kMaxBlocks - 1) / kMaxBlocks);
+        // the deterministic reduction keeps one partial per block: cap the grid at kMaxBlocks
+        const int max_gy = kMaxBlocks / (int)grid.x;
+        if (max_gy < 1) return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");
+        g.rows = (ny + max_gy - 1) / max_gy;
         grid.y = (ny + g.rows - 1) / g.rows;
     }
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};

@@ -1,0 +1,121 @@
+"""GPU tests at BASELINE.json's full sizes.  The CPU oracle is too slow there, so the CUDA
+path is compared with an independent plain-PyTorch FP64 implementation of the same
+recurrences run on the same GPU (eager torch ops, stencil by padding/slicing), plus
+size-independent properties of the manufactured problem (b in {0,1,2}, ||b|| = sqrt(4n+8))."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = (8.2, 0.2)
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import gmres_b200 as kl
+    h = kl.Handle(0)
+    h.set_option(3, 0)   # no v_err epilogue at these sizes
+    yield kl, h, torch
+    h.close()
+
+
+def t_apply(torch, x, nx, ny, ex=1.0, ey=1.0, poisson=True):
+    X = x.view(ny, nx)
+    Pd = torch.nn.functional.pad(X, (1, 1, 1, 1))
+    l, r, dn, up = Pd[1:-1, :-2], Pd[1:-1, 2:], Pd[2:, 1:-1], Pd[:-2, 1:-1]
+    if poisson:
+        return (4.0 * X - (((l + r) + dn) + up)).reshape(-1)
+    return (2.0 * (ex + ey) * X - (ex * (l + r) + ey * (dn + up))).reshape(-1)
+
+
+def t_cbpr2(torch, A, r, params):
+    emin, emax = params
+    c, d = (emax - emin) / 2.0, (emax + emin) / 2.0
+    alpha = 1.0 / (d - (c * (1.0 / d) / 2.0) ** 2)
+    z = r / d
+    return z + alpha * (r - A(z))
+
+
+def test_cg_16384_vs_torch_fp64(env):
+    kl, h, torch = env
+    n = 16384
+    b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
+    assert float(b.sum()) == 4.0 * n and float(b.max()) == 2.0 and float(b.min()) == 0.0
+    assert float(torch.linalg.vector_norm(b)) == pytest.approx(np.sqrt(4 * n + 8), rel=1e-14)
+    iters = 40
+    h.set_option(4, iters)
+    g = h.cg_omp(kl.stvec, b, 0.0, iters, nx=n, ny=n)
+    # torch FP64 reference of cg.f90:83-152
+    A = lambda v: t_apply(torch, v, n, n)
+    x = torch.zeros_like(b); r = b.clone(); p = b.clone(); hist = []
+    for _ in range(iters):
+        ax = A(p); rr = torch.dot(r, r); alpha = rr / torch.dot(ax, p)
+        x += alpha * p; r -= alpha * ax
+        rn = torch.dot(r, r); hist.append(float(torch.sqrt(rn)))
+        p = r + (rn / rr) * p
+    hist = np.array(hist)
+    rel = np.abs(g.history / hist - 1)
+    print("cg16384 history rel diff", rel.max())
+    assert g.history.size == iters and rel.max() < 1e-10
+    assert float((g.x - x).abs().max()) < 1e-11
+
+
+def test_pbicgstab_aniso_8192_vs_torch_fp64(env):
+    kl, h, torch = env
+    n = 8192
+    A_k = kl.aniso(1.0, 0.01)
+    b = h.apply(A_k, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
+    A = lambda v: t_apply(torch, v, n, n, 1.0, 0.01, poisson=False)
+    M = lambda v: t_cbpr2(torch, A, v, P)
+    iters = 12
+    h.set_option(4, iters)
+    g = h.pbicgstab_omp(A_k, b, 0.0, iters, kl.cbpr2, P, nx=n, ny=n)
+    x = torch.zeros_like(b); r = b.clone(); r0 = b.clone(); p = b.clone(); hist = []
+    for _ in range(iters):          # bicgstab.f90:91-182
+        z1 = M(p); ap = A(z1); rr0 = torch.dot(r, r0); alpha = rr0 / torch.dot(ap, r0)
+        s = r - alpha * ap; z2 = M(s); as_ = A(z2)
+        omega = torch.dot(as_, s) / torch.dot(as_, as_)
+        x = x + alpha * z1 + omega * z2; r = s - omega * as_
+        hist.append(float(torch.linalg.vector_norm(r)))
+        beta = (torch.dot(r, r0) / rr0) * (alpha / omega)
+        p = r + beta * (p - omega * ap)
+    rel = np.abs(g.history / np.array(hist) - 1)
+    print("pbicgstab8192 history rel diff", rel)
+    assert rel[:6].max() < 1e-9 and rel.max() < 1e-5
+    assert float((g.x - x).abs().max()) < 1e-6
+
+
+def test_gmres_mgsr_4096_cycle_vs_torch_fp64(env):
+    kl, h, torch = env
+    n, m = 4096, 24
+    b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
+    h.set_option(2, 1)    # one restart cycle
+    try:
+        g = h.gmres_mgsr_omp(kl.stvec, b, m, 0.0, kl.cbpr2, P, nx=n, ny=n)
+    finally:
+        h.set_option(2, 1000)
+    A = lambda v: t_apply(torch, v, n, n)
+    M = lambda v: t_cbpr2(torch, A, v, P)
+    beta0 = float(torch.linalg.vector_norm(b))
+    w = M(b)
+    beta = torch.linalg.vector_norm(w)
+    V = [w / beta]
+    H = np.zeros((m + 1, m)); gvec = np.zeros(m + 1); gvec[0] = float(beta)
+    cs = np.zeros(m); sn = np.zeros(m); fe = []
+    for j in range(m):               # gmres_mgsr.f90:333-391 (MGS twice)
+        w = M(A(V[j]))
+        for _ in range(2):
+            for i in range(j + 1):
+                hh = torch.dot(w, V[i]); H[i, j] += float(hh); w = w - hh * V[i]
+        hv = float(torch.linalg.vector_norm(w)); H[j + 1, j] = hv
+        for i in range(j):
+            t = H[i, j]; H[i, j] = cs[i] * t + sn[i] * H[i + 1, j]; H[i + 1, j] = -sn[i] * t + cs[i] * H[i + 1, j]
+        ds = np.hypot(H[j + 1, j], H[j, j]); cs[j] = H[j, j] / ds; sn[j] = H[j + 1, j] / ds
+        H[j, j] = cs[j] * H[j, j] + sn[j] * H[j + 1, j]; H[j + 1, j] = 0
+        t = gvec[j]; gvec[j] = cs[j] * t + sn[j] * gvec[j + 1]; gvec[j + 1] = -sn[j] * t + cs[j] * gvec[j + 1]
+        fe.append(abs(gvec[j + 1]) / beta0)
+        V.append(w / hv)
+    rel = np.abs(g.history[:m] / np.array(fe) - 1)
+    print("gmres4096 cycle history rel diff", rel.max())
+    assert g.n_out == m and rel.max() < 1e-10
+    assert np.all(np.diff(g.history[:m]) <= 0)     # GMRES residual estimate is monotone within a cycle
