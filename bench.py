@@ -288,6 +288,8 @@ def gpu_arm(args):
             "config": {"workload": f"{w['solver']} Poisson 2D 5-point {primary['nx']}x{primary['ny']} "
                                    f"({primary['n_unknowns']} unknowns), tol=0 (fixed K iterations)",
                        "name": args.workload, "partition": f"row-slab x{world}",
+                       "comm": ("none" if world == 1 else ("nvlink-peer-memory (IPC) all-reduce + halo push"
+                                                            if h.get_option(10) else "nccl send/recv + allreduce")),
                        "l2": "inputs larger than L2 (no flush needed)", "bytes_per_iteration": primary["bytes_per_iter"]},
             "clocks": primary["clocks"], "gpu_launches": primary["launches"],
             "roofline": primary.get("roofline"), "roofline_iter": primary["roofline_iter"],

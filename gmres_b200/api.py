@@ -247,6 +247,11 @@ class Handle:
     def set_option(self, key: int, value: int):
         self._chk(self._L.kl_set_option(self._h, key, int(value)))
 
+    def get_option(self, key: int) -> int:
+        v = C.c_int()
+        self._chk(self._L.kl_get_option(self._h, key, C.byref(v)))
+        return v.value
+
     def set_ortho(self, mode: int):
         self.set_option(KL_OPT_ORTHO, mode)
 

@@ -66,8 +66,10 @@ struct kl_context_s;
 namespace kl {
 using Ctx = ::kl_context_s;
 int comm_allreduce(Ctx *c, double *d_buf, int count);
+// exchanges the boundary lines of nvec slab vectors; lo_out/hi_out receive the halo line pointers
+// (nullptr at the global boundary)
 int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *const *send_hi_rows,
-                       double *const *recv_lo, double *const *recv_hi, int nvec, int nx);
+                       const double **lo_out, const double **hi_out, int nvec, int nx);
 
 }  // namespace kl
 
@@ -91,6 +93,12 @@ struct kl_context_s {
     // comm
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
+    // NVLink peer-memory collectives (one-shot all-reduce and halo push over IPC-mapped buffers)
+    int opt_peer = 1;
+    bool peer_ok = false;
+    double *cb_local = nullptr;          // this rank's communication buffer
+    double *cb_peer[16] = {};            // every rank's buffer mapped into this process (cb_peer[rank] = cb_local)
+    unsigned long long ar_seq = 0, halo_seq = 0;
     // device blocks
     double *d_S = nullptr;
     int *d_I = nullptr;

@@ -51,17 +51,12 @@ int halo_exchange(Prob *P, const double *const *vecs, int nvec, Halo *H) {
     if (c->nranks == 1) return KL_OK;
     if (nvec > 4) return c->fail(KL_ERR_INVALID, "halo_exchange: too many vectors");
     const double *slo[4], *shi[4];
-    double *rlo[4], *rhi[4];
     for (int a = 0; a < nvec; ++a) {
         slo[a] = vecs[a];
         shi[a] = vecs[a] + (size_t)(P->nyl - 1) * P->nx;
-        rlo[a] = c->d_halo + (size_t)(2 * a) * P->nx;
-        rhi[a] = c->d_halo + (size_t)(2 * a + 1) * P->nx;
-        H->lo[a] = c->rank > 0 ? rlo[a] : nullptr;
-        H->hi[a] = c->rank < c->nranks - 1 ? rhi[a] : nullptr;
     }
     // NOTE: a stencil kernel treats lo[0]==nullptr as "no lower neighbour" for all inputs.
-    return comm_halo_exchange(c, slo, shi, rlo, rhi, nvec, P->nx);
+    return comm_halo_exchange(c, slo, shi, H->lo, H->hi, nvec, P->nx);
 }
 
 int op_apply(Prob *P, const double *x, double *y, bool gated) {

@@ -111,7 +111,9 @@ enum {
     KL_OPT_HH_MODE = 6,       /* Householder application, see below                  */
     KL_OPT_FUSE = 7,          /* 1 (default): fused kernels; 0: one kernel per reference loop */
     KL_OPT_PROFILE = 8,       /* 1: CUDA-event pairs around every hot kernel (kl_get_profile)  */
-    KL_OPT_TMA = 9            /* 1 (default): TMA-staged stencil kernels; 0: register-pipelined ones */
+    KL_OPT_TMA = 9,           /* 1 (default): TMA-staged stencil kernels; 0: register-pipelined ones */
+    KL_OPT_PEER = 10          /* multi-GPU: 1 = NVLink peer-memory all-reduce / halo push (default when the
+                                 IPC mapping succeeded), 0 = NCCL collectives.  Set on all ranks alike. */
 };
 enum {
     KL_ORTHO_MGS2 = 0,  /* the reference's modified Gram-Schmidt applied twice (gmres_mgsr.f90:341-360) */

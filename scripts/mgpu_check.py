@@ -14,6 +14,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 h = init_handle(local)
 h1 = kl.Handle(local)          # single-GPU reference on every rank (same device)
 ok = True
+if rank == 0:
+    print("peer-memory collectives:", bool(h.get_option(10)), flush=True)
 
 def gather(xl, nx, ny):
     parts = [None] * world
