@@ -58,7 +58,7 @@ class kl_stats_t(C.Structure):
     _fields_ = [("iterations", C.c_int), ("cycles", C.c_int), ("solve_ms", C.c_double),
                 ("total_ms", C.c_double), ("algorithmic_bytes", C.c_double),
                 ("kernel_launches", C.c_longlong), ("orth_frobenius", C.c_double),
-                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("reorth_skipped", C.c_int)]
 
 
 class KrylovError(RuntimeError):

@@ -515,6 +515,10 @@ int kl_set_option(kl_handle_t h, int key, int value) {
         case KL_OPT_FUSE: h->opt_fuse = value != 0; break;
         case KL_OPT_PROFILE: h->opt_profile = value != 0; break;
         case KL_OPT_TMA: h->opt_tma = value != 0; break;
+        case KL_OPT_REORTH_ETA:
+            if (value < 1 || value > 1000) return KL_ERR_INVALID;
+            h->opt_reorth_eta_permille = value;
+            break;
         case KL_OPT_PEER:
             // all ranks must switch together; only meaningful before / between solves
             if (value && !h->cb_local) return KL_ERR_INVALID;
@@ -537,6 +541,7 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_FUSE: *value = h->opt_fuse; break;
         case KL_OPT_PROFILE: *value = h->opt_profile; break;
         case KL_OPT_TMA: *value = h->opt_tma; break;
+        case KL_OPT_REORTH_ETA: *value = h->opt_reorth_eta_permille; break;
         case KL_OPT_PEER: *value = h->peer_ok ? 1 : 0; break;
         default: return KL_ERR_INVALID;
     }

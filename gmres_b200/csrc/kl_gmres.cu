@@ -29,10 +29,35 @@
 
 namespace kl {
 
-__global__ void k_givens(const GmresDev G, const int j) {
+__global__ void k_givens(const GmresDev G, const int j, const int honor_skip = 0) {
     extern __shared__ double sm[];
     if (G.I[I_CONV_AT] >= 0) return;
+    if (honor_skip && G.I[I_SKIP3]) return;
     givens_update_warp(G, j, sqrt(G.S[S_RED]), threadIdx.x, sm);
+}
+
+// Selective reorthogonalisation (KL_ORTHO_CGS2_SELECTIVE).  After  w' = w - V h1 ,  h2 = V^T w'  with
+// ww = ||w||^2 (h1[nc]) and ww1 = ||w'||^2 (h2[nc]): if ||w'|| >= eta ||w|| the first pass lost at most
+// a factor 1/eta of accuracy and the second update is skipped (h2 is discarded, ||w'|| is the new
+// sub-diagonal); otherwise H(:,j) += h2 and the second update pass runs.  One warp, replicated on every rank.
+__global__ void k_select(const GmresDev G, const double *h1, const double *h2, const int j, const int nc,
+                         const double eta2) {
+    extern __shared__ double sm[];
+    if (G.I[I_CONV_AT] >= 0) return;
+    const double ww = h1[nc], ww1 = h2[nc];
+    const bool skip = ww1 >= eta2 * ww;
+    if (skip) {
+        if (threadIdx.x == 0) {
+            G.I[I_SKIP3] = 1;
+            G.I[I_NSKIP] = G.I[I_NSKIP] + 1;
+            G.I[I_NSKIPCOLS] = G.I[I_NSKIPCOLS] + nc;
+        }
+        givens_update_warp(G, j, sqrt(ww1), threadIdx.x, sm);
+    } else {
+        double *Hj = G.H + (size_t)j * G.ldh;
+        for (int c = threadIdx.x; c < nc; c += 32) Hj[c] = Hj[c] + h2[c];
+        if (threadIdx.x == 0) G.I[I_SKIP3] = 0;
+    }
 }
 
 // H(0..ncols-1, j) (+)= hvec   (gmres_mgsr.f90:351-353)
@@ -157,7 +182,9 @@ __global__ void __launch_bounds__(kTsThreads)
 k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n, const int ncols,
        const double *__restrict__ h, const RedCtl rc, const int want_norm, const GmresDev G,
        const int j, const int fuse_givens, const int *__restrict__ flags) {
+    // want_norm: bit 0 = reduce ||w||^2 ; bit 1 = selective mode: do nothing when I_SKIP3 is set
     if (flags && flags[I_CONV_AT] >= 0) return;
+    if ((want_norm & 2) && flags[I_SKIP3]) return;
     extern __shared__ double sm[];   // max(ncols, 3*(m+2)) doubles + reduction scratch
     double *sh = sm;
     for (int c = threadIdx.x; c < ncols; c += kTsThreads) sh[c] = h[c];
@@ -210,7 +237,7 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
 #pragma unroll
         for (int e = 0; e < VEC; ++e) nacc = fma(a[e], a[e], nacc);
     }
-    if (!want_norm) return;
+    if (!(want_norm & 1)) return;
     __syncthreads();
     __shared__ double s_red[kTsWarps];
     __shared__ int s_flag;
@@ -382,23 +409,24 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
 }
 
 int launch_wmvh(Ctx *c, const double *V, size_t ldv, double *w, size_t n, int ncols, const double *h,
-                bool want_norm, const GmresDev &G, int j, bool givens, bool gated) {
+                bool want_norm, const GmresDev &G, int j, bool givens, bool gated, bool honor_skip = false) {
     const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
     const int grid = upd_grid(n / vec);
     const size_t smem = sizeof(double) * std::max(ncols + 8, 3 * (G.m + 2));
     const int fuse = (givens && c->nranks == 1) ? 1 : 0;
+    const int wn = (want_norm ? 1 : 0) | (honor_skip ? 2 : 0);
     RedCtl rc = redctl(c);
     if (vec == 2)
-        k_wmvh<2><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, want_norm, G, j, fuse,
-                                                         gated ? c->d_I : nullptr);
+        k_wmvh<2><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, wn, G, j, fuse,
+                                                         (gated || honor_skip) ? c->d_I : nullptr);
     else
-        k_wmvh<1><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, want_norm, G, j, fuse,
-                                                         gated ? c->d_I : nullptr);
+        k_wmvh<1><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, wn, G, j, fuse,
+                                                         (gated || honor_skip) ? c->d_I : nullptr);
     c->stats.kernel_launches++;
     if (want_norm && c->nranks > 1) {
         KL_TRY(comm_allreduce(c, c->d_S + S_RED, 1));
         if (givens) {
-            k_givens<<<1, 32, sizeof(double) * 3 * (G.m + 2), c->stream>>>(G, j);
+            k_givens<<<1, 32, sizeof(double) * 3 * (G.m + 2), c->stream>>>(G, j, honor_skip ? 1 : 0);
             c->stats.kernel_launches++;
         }
     }
@@ -557,7 +585,18 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
                 }
                 bytes += (32.0 * total + 24.0) * n;
             } else {
-                if (ts_tma_ok(c, n, ldv, ncols)) {
+                if (c->opt_ortho == KL_ORTHO_CGS2_SELECTIVE && ts_tma_ok(c, n, ldv, ncols)) {
+                    const double eta = c->opt_reorth_eta_permille * 1e-3;
+                    { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
+                      KL_TRY(launch_ts_tma(c, false, V, ldv, m + 1, wj, n, ncols, nullptr, G.hvec, G, j, 1, true, 0)); }
+                    { ProfScope ps(c, 4, "gmres_wmvh_vtw_tma (w-=V h1 fused with h2=V^T w)", (8.0 * ncols + 16.0) * n);
+                      KL_TRY(launch_ts_tma(c, true, V, ldv, m + 1, wj, n, ncols, G.hvec, G.hvec2, G, j, 0, true, 0)); }
+                    k_select<<<1, 32, sizeof(double) * 3 * (m + 2), c->stream>>>(G, G.hvec, G.hvec2, j, ncols, eta * eta);
+                    c->stats.kernel_launches++;
+                    { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
+                      KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec2, true, G, j, true, true, true)); }
+                    bytes += (24.0 * ncols + 40.0) * n;
+                } else if (ts_tma_ok(c, n, ldv, ncols)) {
                     // 3 passes over V: project ; update + project (fused, V tile staged once) ; update + norm
                     { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
                       KL_TRY(launch_ts_tma(c, false, V, ldv, m + 1, wj, n, ncols, nullptr, G.hvec, G, j, 1, true)); }
@@ -647,7 +686,10 @@ static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, dou
     c->stats.cycles = cycles;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
+    // selective reorthogonalisation: the skipped second update passes moved no data
+    bytes -= (8.0 * c->h_pinned_i[I_NSKIPCOLS] + 16.0 * c->h_pinned_i[I_NSKIP]) * (double)n;
     c->stats.algorithmic_bytes = bytes;
+    c->stats.reorth_skipped = c->h_pinned_i[I_NSKIP];
     *n_out_p = n_out;
     *restart_out_p = restart_out;
     return status;

@@ -49,6 +49,9 @@ enum IIdx {
     I_HIST,          // number of history entries written
     I_BREAKDOWN,
     I_STEP,
+    I_SKIP3,         // selective reorthogonalisation: 1 = the second update pass of this step is skipped
+    I_NSKIP,         // number of skipped second passes ; I_NSKIPCOLS = sum of their column counts
+    I_NSKIPCOLS,
     I_COUNT = 64
 };
 
@@ -89,6 +92,7 @@ struct kl_context_s {
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_tma = 1;
+    int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
     // comm
     int rank = 0, nranks = 1;

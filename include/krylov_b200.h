@@ -112,13 +112,15 @@ enum {
     KL_OPT_FUSE = 7,          /* 1 (default): fused kernels; 0: one kernel per reference loop */
     KL_OPT_PROFILE = 8,       /* 1: CUDA-event pairs around every hot kernel (kl_get_profile)  */
     KL_OPT_TMA = 9,           /* 1 (default): TMA-staged stencil kernels; 0: register-pipelined ones */
+    KL_OPT_REORTH_ETA = 11,   /* KL_ORTHO_CGS2_SELECTIVE threshold eta in 1/1000 (default 707 = 1/sqrt2):
+                                 the second Gram-Schmidt pass runs only when ||w'|| < eta ||w||          */
     KL_OPT_PEER = 10          /* multi-GPU: 1 = NVLink peer-memory all-reduce / halo push (default when the
                                  IPC mapping succeeded), 0 = NCCL collectives.  Set on all ranks alike. */
 };
 enum {
     KL_ORTHO_MGS2 = 0,  /* the reference's modified Gram-Schmidt applied twice (gmres_mgsr.f90:341-360) */
     KL_ORTHO_CGS2 = 1,  /* classical Gram-Schmidt twice: h = V^T w one-pass kernels (default)           */
-    KL_ORTHO_CGS2_SELECTIVE = 2 /* CGS with the second pass only when ||w'|| < eta ||w||  */
+    KL_ORTHO_CGS2_SELECTIVE = 2 /* CGS with the second update only when ||w'|| < eta ||w|| (device-side test) */
 };
 enum {
     KL_HH_SEQUENTIAL = 0, /* reflector by reflector, the reference's order (gmres_hh.f90:269-304) */
@@ -224,6 +226,7 @@ typedef struct {
     long long kernel_launches;
     double orth_frobenius;   /* ||I - V^T V||_F of the last basis when KL_OPT_VERR */
     double h2d_bytes, d2h_bytes;
+    int reorth_skipped;      /* KL_ORTHO_CGS2_SELECTIVE: second passes skipped            */
 } kl_stats_t;
 int kl_get_stats(kl_handle_t h, kl_stats_t *out);
 /* per-kernel-class timers of the last solve (KL_OPT_PROFILE = 1): class idx in

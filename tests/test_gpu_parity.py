@@ -346,3 +346,31 @@ def test_gmres_hh_blocked_compact_wy(kl, h, ko, ns, m):
     assert g.v_err.max() < 1e-27 and g.stats["orth_frobenius"] < 1e-11
     if g0 is not None:
         assert g0.status == 0 and np.abs(g0.x - 1).max() < 1e-4
+
+
+@pytest.mark.parametrize("ns,m", [(100, 95), (300, 95)])
+def test_gmres_selective_reorthogonalisation(kl, h, ko, ns, m):
+    """KL_ORTHO_CGS2_SELECTIVE (north star item 2): the second Gram-Schmidt update runs only when
+    ||w'|| < eta ||w|| (decided on the device).  eta = 1/sqrt(2) (default, "twice is enough") keeps the
+    basis orthogonal to machine precision; a small eta trades orthogonality (~eps/eta^2 per step) for
+    one V pass less per step.  Either way the iteration count matches the reference's always-twice scheme."""
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    o = ko.gmres_mgsr_omp(ko.stvec_fn(), b, m, 1e-8, ko.cbpr2_fn(), P)
+    oi = _its(o, m)
+    h.set_ortho(2)
+    try:
+        g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
+        h.set_option(11, 100)     # eta = 0.1
+        g1 = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
+    finally:
+        h.set_option(11, 707)
+        h.set_ortho(1)
+    for tag, r in (("eta=0.707", g), ("eta=0.1", g1)):
+        print(f"selective ns={ns} {tag}: its {_its(r, m)} (oracle {oi}), skipped {r.stats['reorth_skipped']} of "
+              f"{r.stats['iterations']}, ||I-VtV||_F {r.stats['orth_frobenius']:.2e}")
+        assert r.status == 0 and abs(_its(r, m) - oi) <= 1
+        assert np.abs(r.x - o.x).max() < 1e-7
+    assert g.stats["orth_frobenius"] < 1e-11
+    k = min(g.history.size, o.history.size)
+    assert np.abs(g.history[:k] / o.history[:k] - 1).max() < 1e-6
+    assert g1.stats["reorth_skipped"] > 0.5 * g1.stats["iterations"] and g1.stats["orth_frobenius"] < 1e-4
