@@ -374,3 +374,47 @@ def test_gmres_selective_reorthogonalisation(kl, h, ko, ns, m):
     k = min(g.history.size, o.history.size)
     assert np.abs(g.history[:k] / o.history[:k] - 1).max() < 1e-6
     assert g1.stats["reorth_skipped"] > 0.5 * g1.stats["iterations"] and g1.stats["orth_frobenius"] < 1e-4
+
+
+@pytest.mark.parametrize("ns", [37, 50])
+def test_small_and_odd_grids_take_the_generic_kernels(kl, h, ko, ns):
+    """Odd nx (scalar loads) and nx < 64 (register-pipelined stencil instead of TMA): same results."""
+    A, M = ko.stvec_fn(), ko.cbpr2_fn()
+    b = ko.manufactured_rhs(A, ns)
+    o = ko.pcg_omp(A, b, 1e-9, 5000, M, P)
+    g = h.pcg_omp(kl.stvec, b, 1e-9, 5000, kl.cbpr2, P)
+    assert g.iter == o.iter and np.abs(g.x - o.x).max() < 1e-12
+    og = ko.gmres_mgsr_omp(A, b, 20, 1e-8, M, P)
+    gg = h.gmres_mgsr_omp(kl.stvec, b, 20, 1e-8, kl.cbpr2, P)
+    assert _its(gg, 20) == _its(og, 20) and np.abs(gg.x - og.x).max() < 1e-11
+    oh = ko.gmres_hh(A, b, 20, 1e-8, M, P)
+    gh = h.gmres_hh_prec_omp(kl.stvec, b, 20, 1e-8, kl.cbpr2, P)
+    assert _its(gh, 20) == _its(oh, 20) and np.abs(gh.x - oh.x).max() < 1e-11
+    ob = ko.pbicgstab_omp(A, b, 1e-9, 5000, M, P)
+    gb = h.pbicgstab_omp(kl.stvec, b, 1e-9, 5000, kl.cbpr2, P)
+    assert abs(gb.iter - ob.iter) <= 3 and np.abs(gb.x - 1).max() < 1e-7
+
+
+def test_restart_length_above_96_uses_the_multi_pass_projection(kl, h, ko):
+    """m + 1 > 96 columns: the TMA tall-skinny kernels hand over to the multi-pass k_vtw / k_wmvh."""
+    ns, m = 100, 130
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    o = ko.gmres_mgsr_omp(ko.stvec_fn(), b, m, 1e-10, ko.cbpr2_fn(), P)
+    g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-10, kl.cbpr2, P)
+    assert g.status == 0 and abs(_its(g, m) - _its(o, m)) <= 1
+    assert np.abs(g.x - o.x).max() < 1e-10 and g.stats["orth_frobenius"] < 1e-12
+    oh = ko.gmres_hh(ko.stvec_fn(), b, m, 1e-10, ko.cbpr2_fn(), P)
+    gh = h.gmres_hh_prec_omp(kl.stvec, b, m, 1e-10, kl.cbpr2, P)     # sequential reflectors (m > 96)
+    assert abs(_its(gh, m) - _its(oh, m)) <= 1 and np.abs(gh.x - oh.x).max() < 1e-10
+
+
+def test_error_codes(kl, h):
+    b = np.ones(16)
+    with pytest.raises(kl.KrylovError):
+        h.gmres_mgsr_omp(kl.stvec, b, 0, 1e-8, kl.cbpr2, P)            # m < 1
+    with pytest.raises(kl.KrylovError):
+        h.pcg_omp(kl.stvec, b, 1e-9, 10, kl.cbpr2, (1.0,))             # params(1:2) missing
+    with pytest.raises(kl.KrylovError):
+        h.apply(kl.Operator(7), b, 4, 4)                               # unknown operator kind
+    r = h.cg_omp(kl.stvec, np.zeros(64), 1e-9, 5)                      # b = 0: 0/0 -> reported as breakdown
+    assert r.status in (0, 2)
