@@ -30,9 +30,10 @@ struct PostCgEnd {
     double *hist;
     int hist_cap;
     int precond;  // 0: S_RED[0] = r.r (cg.f90:135-138) ; 1: S_RED[0] = r.z, r.r in S_TMP0 (cg.f90:219-226)
+                  // 2: S_RED[0] = r.r, S_RED[1] = r.z (fused update + preconditioner kernel)
     __device__ __forceinline__ void run() const {
-        double num = S[S_RED];
-        double rr2 = precond ? S[S_TMP0] : num;
+        double num = precond == 2 ? S[S_RED + 1] : S[S_RED];
+        double rr2 = precond == 1 ? S[S_TMP0] : S[S_RED];
         double res = sqrt(rr2);
         S[S_BETA] = num / S[S_RR];
         S[S_RR] = num;
@@ -44,6 +45,44 @@ struct PostCgEnd {
         I[I_HIST] = hl + 1;
         if (res < S[S_TOL]) I[I_CONV_AT] = it;          // cg.f90:144-149
         else if (!(res == res)) { I[I_BREAKDOWN] = 1; I[I_CONV_AT] = it; }
+    }
+};
+
+// PCG with cbpr2: x += alpha p ; r' = r - alpha ax ; z = cbpr2(r') ; r'.r' ; r'.z in ONE stencil pass
+// (cg.f90:206-218).  in[0] = r, in[1] = ax ; r' goes to the other r buffer (neighbouring CTAs still read r).
+struct FPcgUpdate : StencilBase<2, 2> {
+    double *x, *r_new, *z;
+    const double *p;
+    const double *S;
+    double alpha, d, calpha;
+    FastDiv fd;
+    __device__ __forceinline__ void init() {
+        alpha = S[S_ALPHA];
+        fd.set(d);
+    }
+    __device__ __forceinline__ double point(const double (&v)[2]) const { return fd.div(fma(-alpha, v[1], v[0])); }
+    template <int VEC>
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        double vx[VEC], vp[VEC], rn[VEC], zz[VEC];
+        KL_LD(VEC, vp, p, idx)
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(x + idx);
+            vx[0] = t.x; vx[VEC - 1] = t.y;
+        } else {
+            vx[0] = x[idx];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            vx[v] = fma(alpha, vp[v], vx[v]);                 // :208
+            rn[v] = fma(-alpha, raw[1][v], raw[0][v]);        // :209
+            zz[v] = fma(calpha, rn[v] - au[v], cu[v]);        // chebyshev.f90:35
+            acc[0] = fma(rn[v], rn[v], acc[0]);               // :210
+            acc[1] = fma(rn[v], zz[v], acc[1]);               // :216
+        }
+        KL_ST(VEC, x, idx, vx)
+        KL_ST(VEC, r_new, idx, rn)
+        KL_ST(VEC, z, idx, zz)
     }
 };
 
@@ -65,13 +104,16 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
-    const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0);
+    const bool fuse_pc = fused && P.pc.kind == KL_PC_CBPR2;   // update + cbpr2 in one pass (88n B/iteration)
+    const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0) + (fuse_pc ? 1 : 0);
     KL_TRY(ws_reserve(c, nvec * ws_need(n)));
     ws_reset(c);
     double *r = ws_take<double>(c, n), *p0 = ws_take<double>(c, n), *p1 = ws_take<double>(c, n);
     double *ax = ws_take<double>(c, n);
     double *dx = dev ? x : ws_take<double>(c, n);
     double *z = r, *aux = nullptr, *aux2 = nullptr;
+    double *r_alt = fuse_pc ? ws_take<double>(c, n) : nullptr;
+    const Cbpr2Coef cf = fuse_pc ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
     if (prec) {
         z = ws_take<double>(c, n);
         aux = ws_take<double>(c, n);
@@ -130,7 +172,21 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
                 d.a = ax; d.b = pnew; d.c = nullptr; d.d = nullptr;
                 KL_TRY(launch_pointwise(c, d, n, PostCgAlpha{c->d_S}));
             }
-            // ---- K2
+            // ---- K2 (+K3 fused for cbpr2)
+            if (fuse_pc) {
+                ProfScope ps(c, 3, "pcg_update_precond (stencil: x+=alpha p; r-=alpha ax; z=cbpr2(r); r.r; r.z)", 56.0 * n);
+                Halo H;
+                const double *vecs[2] = {r, ax};
+                KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                FPcgUpdate f;
+                set_io(f, &P, vecs, H);
+                set_gate(f, c, true);
+                f.x = dx; f.r_new = r_alt; f.z = z; f.p = pnew; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
+                KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 2}));
+                std::swap(r, r_alt);
+                double *t = pold; pold = pnew; pnew = t;
+                continue;
+            }
             {
                 ProfScope ps(c, 1, "cg_update_xr_dot (pointwise: x+=alpha p; r-=alpha ax; r.r)", 48.0 * n);
                 PCgUpdate u;
@@ -172,7 +228,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     c->stats.cycles = polls;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
-    c->stats.algorithmic_bytes = (double)its * (prec ? 96.0 : 80.0) * (double)n;
+    c->stats.algorithmic_bytes = (double)its * (fuse_pc ? 88.0 : (prec ? 96.0 : 80.0)) * (double)n;
     *res_out = c->h_pinned[S_RES];
     if (status == KL_OK) *iter = c->h_pinned_i[I_CONV_AT];   // count on exit; unchanged if not converged
     return status;
