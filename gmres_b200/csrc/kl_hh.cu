@@ -204,22 +204,28 @@ struct HhWy {
     int ldt, ldy;
 };
 
-// tvec(0..j) = T(0..j,0..j) * Ytop(row, 0..j)      (row = j: v_j ; also used by calculate_verr)
-__global__ void k_wy_pre(const GmresDev G, const HhWy W, const int j, const int gated) {
+// The O(j^2) triangular products use 8 warps: one warp per output element, lanes over the
+// reduction index, shuffle reduction (the one-warp versions took ~10 us each at j ~ 90).
+// tvec(0..j) = T(0..j,0..j) * Ytop(row j, 0..j)      (v_j ; also used by calculate_verr)
+__global__ void __launch_bounds__(256) k_wy_pre(const GmresDev G, const HhWy W, const int j, const int gated) {
     if (gated && G.I[I_CONV_AT] >= 0) return;
-    for (int r = threadIdx.x; r <= j; r += 32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r <= j; r += 8) {
         double t = 0.0;
-        for (int c = r; c <= j; ++c) t = fma(W.T[(size_t)c * W.ldt + r], W.Ytop[(size_t)c * W.ldy + j], t);
-        W.tvec[r] = t;
+        for (int c = r + lane; c <= j; c += 32) t = fma(W.T[(size_t)c * W.ldt + r], W.Ytop[(size_t)c * W.ldy + j], t);
+        t = warp_sum(t);
+        if (lane == 0) W.tvec[r] = t;
     }
 }
 // tvec(0..j) = T(0..j,0..j)^T * svec(0..j)
-__global__ void k_wy_tT(const GmresDev G, const HhWy W, const int j) {
+__global__ void __launch_bounds__(256) k_wy_tT(const GmresDev G, const HhWy W, const int j) {
     if (G.I[I_CONV_AT] >= 0) return;
-    for (int c = threadIdx.x; c <= j; c += 32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = wid; c <= j; c += 8) {
         double t = 0.0;
-        for (int r = 0; r <= c; ++r) t = fma(W.T[(size_t)c * W.ldt + r], W.svec[r], t);
-        W.tvec[c] = t;
+        for (int r = lane; r <= c; r += 32) t = fma(W.T[(size_t)c * W.ldt + r], W.svec[r], t);
+        t = warp_sum(t);
+        if (lane == 0) W.tvec[c] = t;
     }
 }
 // cycle end: svec = Ytop(0..k-1, 0..k-1)^T y ; tvec = T_k svec    (x += [y;0] - Y tvec)
@@ -321,56 +327,55 @@ __global__ void k_hh_first_wy(const GmresDev G, const HhWy W, const double *w) {
     for (int r = lane; r <= G.m; r += 32) W.Ytop[r] = (r == 0 ? pv : w[r]) / nw;
 }
 
-// serial block of the reference in WY form by ONE WARP: H(:,j), Householder pivot, new column of
-// Ytop and of T, Givens update (gmres_hh.f90:305-345).  u = Y^T w (u[0..j]) and the tail sum u[j+1].
-__global__ void k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, const int j,
-                             const int prec_variant) {
+// serial block of the reference in WY form: H(:,j), Householder pivot, new column of Ytop and of T
+// (8 warps), then the Givens update by warp 0 (gmres_hh.f90:305-345).  u = Y^T w (u[0..j]) and the
+// tail sum u[j+1].
+__global__ void __launch_bounds__(256)
+k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, const int j, const int prec_variant) {
     extern __shared__ double sm[];     // 3*(m+2) for Givens + (m+2) for z
     if (G.I[I_CONV_AT] >= 0) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *sh = sm, *sz = sm + 3 * (G.m + 2);
+    __shared__ double s_sc[3];
     double *Hj = G.H + (size_t)j * G.ldh;
-    for (int i = lane; i <= j; i += 32) {          // :306 H(1:j,j) = w(1:j)
+    for (int i = threadIdx.x; i <= j; i += 256) {          // :306 H(1:j,j) = w(1:j)
         const double t = w[i];
         sh[i] = t;
         Hj[i] = t;
     }
-    double hj1 = 0.0, pv = 0.0, nw = 1.0;
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         const double S2 = u[j + 1];
         const double piv = w[j + 1];
-        const double tmp = sqrt(fma(piv, piv, S2));
-        hj1 = (piv > 0.0) ? -tmp : tmp;
-        pv = piv - hj1;
-        nw = sqrt(fma(pv, pv, S2));
+        const double tmp = sqrt(fma(piv, piv, S2));         // :308 norm2(w(j+1:n))
+        const double hj1 = (piv > 0.0) ? -tmp : tmp;        // :309-313
+        const double pv = piv - hj1;                        // :316
+        const double nw = sqrt(fma(pv, pv, S2));            // :317 norm2(w)
         G.S[S_TMP1] = pv;
         G.S[S_NORM] = nw;
+        s_sc[0] = hj1; s_sc[1] = pv; s_sc[2] = nw;
     }
-    hj1 = __shfl_sync(0xffffffffu, hj1, 0);
-    pv = __shfl_sync(0xffffffffu, pv, 0);
-    nw = __shfl_sync(0xffffffffu, nw, 0);
-    __syncwarp();
-    if (j + 1 <= G.m) {
-        // Ytop(:, j+1) = masked w / nw
-        for (int r = lane; r <= G.m; r += 32)
-            W.Ytop[(size_t)(j + 1) * W.ldy + r] = r <= j ? 0.0 : ((r == j + 1 ? pv : w[r]) / nw);
-        // z = Y^T p_{j+1} = (u - sum_{r<=j} Ytop(r,:) w_r - Ytop(j+1,:) hj1) / nw
-        for (int c = lane; c <= j; c += 32) {
-            double t = u[c];
-            for (int r = c; r <= j; ++r) t = fma(-W.Ytop[(size_t)c * W.ldy + r], sh[r], t);
-            t = fma(-W.Ytop[(size_t)c * W.ldy + j + 1], hj1, t);
-            sz[c] = t / nw;
-        }
-        __syncwarp();
-        // T(0..j, j+1) = -2 T z ; T(j+1,j+1) = 2
-        for (int r = lane; r <= j; r += 32) {
-            double t = 0.0;
-            for (int c = r; c <= j; ++c) t = fma(W.T[(size_t)c * W.ldt + r], sz[c], t);
-            W.T[(size_t)(j + 1) * W.ldt + r] = -2.0 * t;
-        }
-        if (lane == 0) W.T[(size_t)(j + 1) * W.ldt + j + 1] = 2.0;
+    __syncthreads();
+    const double hj1 = s_sc[0], pv = s_sc[1], nw = s_sc[2];
+    // Ytop(:, j+1) = masked w / nw
+    for (int r = threadIdx.x; r <= G.m; r += 256)
+        W.Ytop[(size_t)(j + 1) * W.ldy + r] = r <= j ? 0.0 : ((r == j + 1 ? pv : w[r]) / nw);
+    // z = Y^T p_{j+1} = (u - sum_{r<=j} Ytop(r,:) w_r - Ytop(j+1,:) hj1) / nw
+    for (int c = wid; c <= j; c += 8) {
+        double t = 0.0;
+        for (int r = c + lane; r <= j; r += 32) t = fma(W.Ytop[(size_t)c * W.ldy + r], sh[r], t);
+        t = warp_sum(t);
+        if (lane == 0) sz[c] = ((u[c] - t) - W.Ytop[(size_t)c * W.ldy + j + 1] * hj1) / nw;
     }
-    __syncwarp();
+    __syncthreads();
+    // T(0..j, j+1) = -2 T z ; T(j+1,j+1) = 2
+    for (int r = wid; r <= j; r += 8) {
+        double t = 0.0;
+        for (int c = r + lane; c <= j; c += 32) t = fma(W.T[(size_t)c * W.ldt + r], sz[c], t);
+        t = warp_sum(t);
+        if (lane == 0) W.T[(size_t)(j + 1) * W.ldt + r] = -2.0 * t;
+    }
+    if (threadIdx.x == 0) W.T[(size_t)(j + 1) * W.ldt + j + 1] = 2.0;
+    if (wid != 0) return;
     const int conv_before = G.I[I_CONV_AT];
     givens_update_warp(G, j, hj1, lane, sm, false);
     if (lane == 0 && !prec_variant) {
@@ -531,7 +536,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
             if (blocked) {
                 const int nc = j + 1;
                 // v_j = e_j - Y (T Ytop(j,:)^T)
-                k_wy_pre<<<1, 32, 0, c->stream>>>(G, W, j, 1);
+                k_wy_pre<<<1, 256, 0, c->stream>>>(G, W, j, 1);
                 KL_TRY(launch_apply_wy(c, Pm, ldv, nc, W.tvec, 1, j, nullptr, vj, 0, n, true));
                 if (prec) {
                     KL_TRY(op_apply(&P, vj, z, true));
@@ -541,9 +546,9 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                 }
                 // s = Y^T w ; t = T^T s ; w -= Y t fused with u = Y^T w and the tail norm
                 KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true));
-                k_wy_tT<<<1, 32, 0, c->stream>>>(G, W, j);
+                k_wy_tT<<<1, 256, 0, c->stream>>>(G, W, j);
                 KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
-                k_hh_step_wy<<<1, 32, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
+                k_hh_step_wy<<<1, 256, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
                 c->stats.kernel_launches += 3;
                 PHhNewReflector f;
                 set_gate(f, c, true, j, 1);
@@ -641,7 +646,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
         for (int i = 0; i < n_out; ++i) {
             double *Vi = Vb + (size_t)i * ldv;
             if (blocked) {
-                k_wy_pre<<<1, 32, 0, c->stream>>>(G, W, i, 0);
+                k_wy_pre<<<1, 256, 0, c->stream>>>(G, W, i, 0);
                 KL_TRY(launch_apply_wy(c, Pm, ldv, i + 1, W.tvec, 1, i, nullptr, Vi, 0, n, false));
                 continue;
             }
