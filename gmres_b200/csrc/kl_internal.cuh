@@ -578,20 +578,39 @@ inline int finish_reduction(Ctx *c, int nred, const Post &post) {
 #include "kl_stencil_tma.cuh"
 namespace kl {
 
+// Wave-aware CTA geometry: pick the number of lines per CTA so that the CTA count fills whole waves
+// of `resident` concurrently running CTAs (a 2.04-wave grid wastes almost a third of its time), while
+// keeping the two re-read halo lines per CTA cheap.  Returns false if the grid cannot fit kMaxBlocks.
+inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid) {
+    const long gx = (nx + strip - 1) / strip;
+    if (gx > kMaxBlocks) return false;
+    int best_rows = 0;
+    double best = -1.0;
+    const int rmin = ny < 8 ? ny : 8, rmax = ny < 256 ? ny : 256;
+    for (int rows = rmin; rows <= rmax; ++rows) {
+        const long gy = (ny + rows - 1) / rows, blocks = gx * gy;
+        if (blocks > kMaxBlocks) continue;
+        const long waves = (blocks + resident - 1) / resident;
+        double eff = (double)blocks / (double)(waves * resident);   // wave quantisation (and under-filled grids)
+        eff *= (double)rows / (double)(rows + 2);                   // halo lines
+        if (eff > best + 1e-9) { best = eff; best_rows = rows; }
+    }
+    if (best_rows == 0) {   // very tall local grids: fewest lines that still fit the reduction buffer
+        const long max_gy = kMaxBlocks / gx;
+        best_rows = (int)((ny + max_gy - 1) / max_gy);
+    }
+    g->nx = nx; g->ny = ny; g->rows = best_rows;
+    *grid = dim3((unsigned)gx, (unsigned)((ny + best_rows - 1) / best_rows));
+    return true;
+}
+
 template <class F, class Post>
 inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, const Post &post) {
     const int vec = (nx % 2 == 0) ? 2 : 1;
     const bool tma = c->opt_tma && vec == 2 && nx >= 64;
     const int strip = tma ? kTmaStrip : kStencilThreads * vec;
-    Geo g{nx, ny, stencil_rows(nx, ny, vec)};
-    dim3 grid((nx + strip - 1) / strip, (ny + g.rows - 1) / g.rows);
-    if ((long)grid.x * grid.y > kMaxBlocks) {
-        // the deterministic reduction keeps one partial per block: cap the grid at kMaxBlocks
-        const int max_gy = kMaxBlocks / (int)grid.x;
-        if (max_gy < 1) return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");
-        g.rows = (ny + max_gy - 1) / max_gy;
-        grid.y = (ny + g.rows - 1) / g.rows;
-    }
+    Geo g{nx, ny, 0};
+    dim3 grid;
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
     const int fuse = c->nranks == 1;
@@ -600,19 +619,30 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
         for (int a = 0; a < F::NIN; ++a) KL_TRY(tmap_encode(c, &tm.m[a], f.in[a], nx, ny));
     }
     constexpr size_t smem = tma_smem_bytes<F::NIN>();
+#define KL_ST_GEO(KERNEL, SMEM)                                                                     \
+    {                                                                                               \
+        static int occ = 0;                                                                         \
+        if (!occ) {                                                                                 \
+            if (SMEM > 0)                                                                           \
+                cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, kStencilThreads, SMEM) != cudaSuccess || \
+                occ < 1)                                                                            \
+                occ = 4;                                                                            \
+        }                                                                                           \
+        if (!stencil_geometry(nx, ny, strip, (long)occ * kNumSM, &g, &grid))                        \
+            return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");           \
+    }
 #define KL_ST_LAUNCH(OPK)                                                                           \
     if (tma) {                                                                                      \
-        static bool attr_done = false;                                                              \
-        if (!attr_done) {                                                                           \
-            cudaFuncSetAttribute(k_stencil_tma<F, OPK, Post>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)smem);                                                        \
-            attr_done = true;                                                                       \
-        }                                                                                           \
+        KL_ST_GEO((k_stencil_tma<F, OPK, Post>), smem)                                              \
         k_stencil_tma<F, OPK, Post><<<grid, kStencilThreads, smem, c->stream>>>(f, g, rc, post, fuse, tm); \
-    } else if (vec == 2)                                                                            \
+    } else if (vec == 2) {                                                                          \
+        KL_ST_GEO((k_stencil<F, OPK, 2, Post>), 0)                                                  \
         k_stencil<F, OPK, 2, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);  \
-    else                                                                                            \
-        k_stencil<F, OPK, 1, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);
+    } else {                                                                                        \
+        KL_ST_GEO((k_stencil<F, OPK, 1, Post>), 0)                                                  \
+        k_stencil<F, OPK, 1, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);  \
+    }
     switch (op->kind) {
         case KL_OP_POISSON5: KL_ST_LAUNCH(KL_OP_POISSON5) break;
         case KL_OP_POISSON5_BRANCHY: KL_ST_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
@@ -620,6 +650,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
         default: return c->fail(KL_ERR_INVALID, "launch_stencil: not a built-in operator");
     }
 #undef KL_ST_LAUNCH
+#undef KL_ST_GEO
     c->stats.kernel_launches++;
     if (F::NRED > 0) return finish_reduction(c, F::NRED, post);
     return KL_OK;
