@@ -258,7 +258,7 @@ __global__ void k_peer_allreduce(double *buf, const int count, const PeerPtrs pp
 
 // block b = 2*v + dir: dir 0 sends my first line of vector v to rank-1 (its "hi" halo) and waits for
 // rank-1's last line (my "lo" halo); dir 1 the mirror image.
-__global__ void k_peer_halo(const double *const *unused, const PeerPtrs pp, const int rank, const int P, const int nx,
+__global__ void k_peer_halo(const PeerPtrs pp, const int rank, const int P, const int nx,
                             const unsigned long long seq, const double *s0, const double *s1, const double *s2,
                             const double *s3, const double *e0, const double *e1, const double *e2, const double *e3,
                             int *I) {
@@ -325,7 +325,7 @@ int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *
             lo_out[v] = has_lo ? base : nullptr;
             hi_out[v] = has_hi ? base + kHaloNxCap : nullptr;
         }
-        k_peer_halo<<<2 * nvec, 256, 0, c->stream>>>(nullptr, peer_ptrs(c), c->rank, c->nranks, nx, c->halo_seq, s[0],
+        k_peer_halo<<<2 * nvec, 256, 0, c->stream>>>(peer_ptrs(c), c->rank, c->nranks, nx, c->halo_seq, s[0],
                                                      s[1], s[2], s[3], e[0], e[1], e[2], e[3], c->d_I);
         c->stats.kernel_launches++;
         return KL_OK;
