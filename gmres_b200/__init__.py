@@ -33,6 +33,12 @@ from .api import (  # noqa: F401
     HH_BLOCKED,
     library_path,
     load_library,
+    KL_OPT_FUSE,
+    KL_OPT_TMA,
+    KL_OPT_CHAIN,
+    KL_OPT_STENCIL_ROWS,
+    KL_OPT_PROFILE,
+    KL_OPT_CHECK_EVERY,
 )
 
 __all__ = [

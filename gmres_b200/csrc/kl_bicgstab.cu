@@ -9,8 +9,10 @@
 //   K1  p' = r + beta (p - omega ap) ; ap' = A p' ; ap'.r0      reads r,p,ap,r0  writes p',ap'  48n
 //   K2  s = r - alpha ap' ; as = A s ; as.s, as.as              reads r,ap'      writes s,as    32n
 //   K3  x += alpha p' + omega s ; r = s - omega as ; r.r, r.r0  reads x,p',s,as,r0 writes x,r   56n
-//  cbpr2 (184n B): K1/K2 produce z1 = cbpr2(p'), z2 = cbpr2(s) in the same pass and the
-//   operator is applied to z1/z2 by a second stencil kernel carrying the dot products.
+//  cbpr2 (160n B): K1/K2 are temporally blocked chains (kl_chain_tma.cuh): direction update, cbpr2 and the
+//   operator in one pass (ChBiDir 56n, ChBiS 40n), K3 64n.  KL_OPT_CHAIN = 0 / multi GPU (184n B): K1/K2
+//   produce z1 = cbpr2(p'), z2 = cbpr2(s) in one pass and a second stencil kernel applies the operator to
+//   z1/z2 carrying the dot products.
 // p and ap are ping-ponged because neighbouring thread blocks still read the old
 // values while the new ones are written.
 #include <math.h>
@@ -93,6 +95,98 @@ struct FBiS : StencilBase<2, (CB ? 0 : 2)> {
             for (int v = 0; v < VEC; ++v) {
                 acc[0] = fma(au[v], cu[v], acc[0]);  // :141 as.s
                 acc[1] = fma(au[v], au[v], acc[1]);  // :142 as.as
+            }
+        }
+    }
+};
+
+// ---- temporally blocked variants for cbpr2 (kl_chain_tma.cuh): preconditioner and operator in ONE pass ----
+// K1: p' = r + beta (p - omega ap) ; z1 = cbpr2(p') ; ap' = A z1 ; ap'.r0
+//     reads r,p,ap,r0  writes p',z1,ap'  (56n B instead of 40n + 24n)
+struct ChBiDir : ChainBase<3, 2, 1, 1> {
+    double *p_new, *z1, *ap_new;
+    const double *r0;
+    const double *S;
+    double beta, omega, d, calpha;
+    FastDiv fd;
+    __device__ __forceinline__ void init() {
+        beta = S[S_BETA];
+        omega = S[S_OMEGA];
+        fd.set(d);
+    }
+    __device__ __forceinline__ void level0(bool out, size_t idx, const double (&raw)[3][2], double (&u)[2],
+                                           double (&cc)[1][2], double *) const {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double pn = fma(beta, fma(-omega, raw[2][e], raw[1][e]), raw[0][e]);   // bicgstab.f90:176
+            cc[0][e] = pn;
+            u[e] = fd.div(pn);                                                           // chebyshev.f90:28-30
+        }
+        if (out) stg2(p_new + idx, cc[0][0], cc[0][1]);
+    }
+    template <class RAW>
+    __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+                                          const double (&cin)[1][2], RAW, double (&u)[2], double (&cout)[1][2],
+                                          double *acc) const {
+        if (lv == 1) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                u[e] = fma(calpha, cin[0][e] - au[e], up[e]);                            // chebyshev.f90:35
+                cout[0][e] = 0.0;
+            }
+            if (out) stg2(z1 + idx, u[0], u[1]);
+        } else {
+            u[0] = u[1] = 0.0;
+            cout[0][0] = cout[0][1] = 0.0;
+            if (out) {
+                const double2 q = ldg2(r0 + idx);
+                stg2(ap_new + idx, au[0], au[1]);
+                acc[0] = fma(au[0], q.x, acc[0]);                                        // :126
+                acc[0] = fma(au[1], q.y, acc[0]);
+            }
+        }
+    }
+};
+
+// K2: s = r - alpha ap ; z2 = cbpr2(s) ; as = A z2 ; as.s, as.as
+//     reads r,ap  writes s,z2,as  (40n B instead of 32n + 24n)
+struct ChBiS : ChainBase<2, 2, 1, 2> {
+    double *s, *z2, *as;
+    const double *S;
+    double alpha, d, calpha;
+    FastDiv fd;
+    __device__ __forceinline__ void init() { alpha = S[S_ALPHA]; fd.set(d); }
+    __device__ __forceinline__ void level0(bool out, size_t idx, const double (&raw)[2][2], double (&u)[2],
+                                           double (&cc)[1][2], double *) const {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double sv = fma(-alpha, raw[1][e], raw[0][e]);                         // bicgstab.f90:134
+            cc[0][e] = sv;
+            u[e] = fd.div(sv);
+        }
+        if (out) stg2(s + idx, cc[0][0], cc[0][1]);
+    }
+    template <class RAW>
+    __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+                                          const double (&cin)[1][2], RAW, double (&u)[2], double (&cout)[1][2],
+                                          double *acc) const {
+        if (lv == 1) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                u[e] = fma(calpha, cin[0][e] - au[e], up[e]);
+                cout[0][e] = cin[0][e];
+            }
+            if (out) stg2(z2 + idx, u[0], u[1]);
+        } else {
+            u[0] = u[1] = 0.0;
+            cout[0][0] = cout[0][1] = 0.0;
+            if (out) {
+                stg2(as + idx, au[0], au[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    acc[0] = fma(au[e], cin[0][e], acc[0]);                              // :141 as.s
+                    acc[1] = fma(au[e], au[e], acc[1]);                                  // :142 as.as
+                }
             }
         }
     }
@@ -199,6 +293,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     const bool prec = P.pc.kind != KL_PC_NONE;
     const bool cb = P.pc.kind == KL_PC_CBPR2;
     const bool fused = c->opt_fuse && P.builtin_op() && (!prec || cb);
+    const bool chain = fused && cb && chain_ok(c, P.nx);   // cbpr2 and the operator in one pass (160n B/iteration)
     const size_t n = P.n;
     const int maxit = *iter;
     c->stats = kl_stats_t{};
@@ -255,7 +350,15 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                 Halo H;
                 const double *v3[3] = {r, pold, apold};
                 KL_TRY(halo_exchange(&P, v3, 3, &H));
-                if (cb) {
+                if (cb && chain) {
+                    ProfScope ps(c, 0, "bicg_dir_cbpr2_apply_dot (chain: p'=r+beta(p-omega ap); z1=cbpr2(p'); ap'=A z1; ap'.r0)", 56.0 * n);
+                    ChBiDir f;
+                    for (int a = 0; a < 3; ++a) f.in[a] = v3[a];
+                    set_gate(f, c, true);
+                    f.p_new = pnew; f.z1 = z1; f.ap_new = apnew; f.r0 = r0; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
+                    KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, PostBiAlpha{c->d_S}));
+                    zz1 = z1;
+                } else if (cb) {
                     FBiDir<true> f;
                     set_io(f, &P, v3, H);
                     set_gate(f, c, true);
@@ -279,7 +382,15 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                 }
                 const double *v2[2] = {r, apnew};
                 KL_TRY(halo_exchange(&P, v2, 2, &H));
-                if (cb) {
+                if (cb && chain) {
+                    ProfScope ps(c, 1, "bicg_s_cbpr2_apply_dots (chain: s=r-alpha ap'; z2=cbpr2(s); as=A z2; as.s; as.as)", 40.0 * n);
+                    ChBiS f;
+                    for (int a = 0; a < 2; ++a) f.in[a] = v2[a];
+                    set_gate(f, c, true);
+                    f.s = s; f.z2 = z2; f.as = as; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
+                    KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, PostBiOmega{c->d_S}));
+                    zz2 = z2;
+                } else if (cb) {
                     FBiS<true> f;
                     set_io(f, &P, v2, H);
                     set_gate(f, c, true);
@@ -327,13 +438,17 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                 d2.a = as; d2.b = s; d2.c = as; d2.d = as;
                 KL_TRY(launch_pointwise(c, d2, n, PostBiOmega{c->d_S}));
             }
-            PBiUpdate u;
-            set_gate(u, c, true);
-            u.x = dx; u.r = r; u.z1 = zz1; u.z2 = zz2; u.s = s; u.as = as; u.r0 = r0; u.S = c->d_S;
-            KL_TRY(launch_pointwise(c, u, n, PostBiEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap}));
+            {
+                ProfScope ps(c, 2, "bicg_update_xr_dots (pointwise: x+=alpha z1+omega z2; r=s-omega as; r.r; r.r0)",
+                             (prec ? 64.0 : 56.0) * n);
+                PBiUpdate u;
+                set_gate(u, c, true);
+                u.x = dx; u.r = r; u.z1 = zz1; u.z2 = zz2; u.s = s; u.as = as; u.r0 = r0; u.S = c->d_S;
+                KL_TRY(launch_pointwise(c, u, n, PostBiEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap}));
+            }
             if (fused) {
                 std::swap(pold, pnew);
-                if (!cb) std::swap(apold, apnew);
+                if (!cb || chain) std::swap(apold, apnew);   // K1 reads ap and writes ap' in the same kernel
                 else apold = apnew;   // cb: K1 reads ap while a later kernel writes it: same buffer is safe
             }
         }
@@ -361,7 +476,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     c->stats.cycles = polls;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
-    c->stats.algorithmic_bytes = (double)its * (cb ? 184.0 : 136.0) * (double)n;
+    c->stats.algorithmic_bytes = (double)its * (cb ? (chain ? 160.0 : 184.0) : 136.0) * (double)n;
     *res_out = c->h_pinned[S_RES];
     if (status == KL_OK) *iter = c->h_pinned_i[I_CONV_AT];
     return status;

@@ -1,0 +1,403 @@
+// kl_chain_tma.cuh -- temporally blocked ("chained") marching stencil kernel (sm_100a).
+//
+// L dependent applications of the 5-point operator in ONE pass over HBM: the
+// degree-k Chebyshev preconditioner (k applications), cbpr2 o A and A o cbpr2
+// (GMRES / BiCGSTAB) read their inputs once and write their outputs once, no
+// matter how many operator applications lie in between.
+//
+// Geometry.  A CTA of 4 warps owns a strip of 4*(64-2H) columns, H = L rounded
+// up to even, and marches down `rows` grid lines.  Every WARP is independent: it
+// owns a 64-column window (lane l: window columns 2l, 2l+1) whose outer H
+// columns are halo -- level l of the chain is valid on window columns
+// [l, 64-l), so left/right neighbours always come from warp shuffles and no
+// inter-warp exchange or CTA barrier is needed inside the march.  In the march
+// direction level l runs l lines behind level 0: when input line R arrives,
+// level l produces line R-l from lines R-l-1, R-l, R-l+1 of level l-1, which sit
+// in registers (3-line window per level, rotated by compile-time phase: the
+// march is unrolled 6 = lcm(3,2) lines so no register moves are executed).  A
+// CTA therefore reads rows+2L lines to write rows lines; overlapping lines and
+// columns are L2 hits (neighbouring CTAs run concurrently), DRAM sees every
+// input once.
+//
+// Input lines arrive through a ring of shared-memory stages filled by 2-D TMA
+// box loads (box = BWP columns x SR lines per input array, full/empty mbarrier
+// pair per stage, one elected producer thread).  The ring keeps the last L lines
+// alive, so level l re-reads raw inputs (e.g. the Chebyshev right-hand side r)
+// at its own line with one LDS.128 instead of carrying them through registers.
+// TMA's out-of-bounds zero fill supplies the zero-Dirichlet boundary for level
+// 0; levels >= 1 are forced to zero outside the domain (those points are not
+// unknowns).
+//
+// Chain functor contract (see ChCheb below and kl_bicgstab.cu / kl_gmres.cu):
+//   NIN, L, NC, NRED               inputs, levels, carried values per point, reductions
+//   void init()
+//   void level0(bool out, size_t idx, const double (&raw)[NIN][2], double (&u)[2], double (&cc)[NC][2], double *acc)
+//        u = level-0 field at the two points of this thread, cc = carried values;
+//        `out`: the points are in the CTA's output range (store level-0 outputs)
+//   template <class RAW>
+//   void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+//              const double (&cin)[NC][2], RAW raw, double (&u)[2], double (&cout)[NC][2], double *acc)
+//        lv in 1..L ; up = field of level lv-1, au = A up ; raw(a) = double2 of input a at this line
+// level0 must map all-zero inputs to u = 0 (outside the domain TMA delivers zeros).
+#pragma once
+#include <type_traits>
+
+#include "kl_stencil_tma.cuh"
+
+namespace kl {
+
+constexpr int kChainWarps = 4;
+constexpr int kChainThreads = kChainWarps * 32;
+constexpr int kChainMaxL = 6;
+
+template <int L>
+struct ChainDims {
+    static constexpr int H = (L + 1) & ~1;              // halo columns per window side
+    static constexpr int WW = 64 - 2 * H;               // output columns per warp
+    static constexpr int STRIP = kChainWarps * WW;      // output columns per CTA
+    static constexpr int BW = STRIP + 2 * H;            // columns a CTA needs
+    static constexpr int BWP = (BW + 15) & ~15;         // TMA box width (row pitch multiple of 128 B)
+};
+template <int NIN, int L>
+struct ChainRing {
+    static constexpr int SR = (NIN == 1) ? 6 : 2;       // lines per stage
+    static constexpr int NST = (NIN == 1) ? 4 : 6;      // stages
+    static constexpr int NR = SR * NST;                 // ring lines (multiple of 6)
+    static constexpr int RET = (L + SR - 1) / SR;       // stages kept alive behind the current one
+    static_assert(NR % 6 == 0, "ring must hold whole hexads");
+    static_assert(NST - RET >= 2, "ring too shallow");
+    static constexpr size_t bytes = (size_t)NIN * NR * ChainDims<L>::BWP * sizeof(double) + 2 * NST * 8 + 64;
+};
+
+struct ChainGeo {
+    int nx, ny, rows;
+    int row_lo, row_hi;    // lines of the domain this rank can see: [row_lo, row_hi) (single GPU: 0, ny)
+};
+
+template <int NIN_, int L_, int NC_, int NRED_>
+struct ChainBase {
+    static constexpr int NIN = NIN_;
+    static constexpr int L = L_;
+    static constexpr int NC = NC_;
+    static constexpr int NRED = NRED_;
+    static_assert(L_ >= 1 && L_ <= kChainMaxL, "chain length");
+    const double *in[NIN_];
+    const int *flags;
+    int step;
+    int run_on_conv;
+    OpCoef coef;
+    __device__ __forceinline__ bool skip() const {
+        if (!flags) return false;
+        int ca = flags[I_CONV_AT];
+        return !(ca < 0 || (run_on_conv && ca == step));
+    }
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 5-point operator, same rounding as apply5 with one instruction less: 4*c is exact, so
+// fma(4, c, -s) == 4*c - s bit for bit (poisson.f90:42, :88-92).
+template <int OPK>
+__device__ __forceinline__ double apply5c(double c, double l, double r, double dn, double up, const OpCoef &k) {
+    if (OPK == KL_OP_POISSON5) {
+        return fma(4.0, c, -(((l + r) + dn) + up));
+    } else if (OPK == KL_OP_POISSON5_BRANCHY) {
+        return ((fma(4.0, c, -l) - r) - up) - dn;
+    } else {
+        double sx = l + r, sy = dn + up;
+        double t = fma(k.ex, sx, k.ey * sy);
+        return fma(k.cc, c, -t);
+    }
+}
+
+template <class C, int OPK>
+__global__ void __launch_bounds__(kChainThreads)
+k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_constant__ TMaps<C::NIN> tm) {
+    if (c_in.skip()) return;
+    C f = c_in;
+    f.init();
+    constexpr int NIN = C::NIN, L = C::L, NC = C::NC, NRED = C::NRED;
+    constexpr int NR_ = NRED > 0 ? NRED : 1;
+    using D = ChainDims<L>;
+    using RG = ChainRing<NIN, L>;
+    constexpr int H = D::H, WW = D::WW, BWP = D::BWP;
+    constexpr int SR = RG::SR, NST = RG::NST, NR = RG::NR, RET = RG::RET;
+    constexpr unsigned kStageBytes = NIN * SR * BWP * sizeof(double);
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                       // [NIN][NR][BWP]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NIN * NR * BWP * sizeof(double));
+    unsigned long long *empty = full + NST;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = blockIdx.x * D::STRIP;            // first output column of the CTA
+    const int bc = wid * WW + 2 * lane;              // this thread's column pair inside the box
+    const int gc = i0 - H + bc;                      // ... and in the grid
+    const bool colin0 = gc >= 0 && gc < g.nx, colin1 = gc + 1 >= 0 && gc + 1 < g.nx;
+    const bool outlane = lane >= H / 2 && lane < 32 - H / 2 && gc < g.nx;
+    const int j0 = blockIdx.y * g.rows;
+    const int j1 = min(j0 + g.rows, g.ny);
+    const int jstart = j0 - L;                       // grid line of march step 0
+    const int T = (j1 - j0) + 2 * L;                 // march steps
+    const int nstg = (T + SR - 1) / SR;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kChainWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int q) {
+        const int s = q % NST;
+        mbar_expect_tx(&full[s], kStageBytes);
+#pragma unroll
+        for (int a = 0; a < NIN; ++a)
+            tma_load_2d(ring + ((size_t)a * NR + (size_t)s * SR) * BWP, &tm.m[a], &full[s], i0 - H, jstart + q * SR);
+    };
+    if (tid == 0) {
+        for (int q = 0; q < NST && q < nstg; ++q) issue(q);
+    }
+
+    double acc[NR_];
+#pragma unroll
+    for (int k = 0; k < NR_; ++k) acc[k] = 0.0;
+    // register windows: U[l][slot][e] = field of level l (l < L), 3 lines ; CC[l][slot][k][e] carried values, 2 lines
+    double U[L][3][2], CC[L][2][NC][2];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) U[l][s][0] = U[l][s][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int k = 0; k < NC; ++k) CC[l][s][k][0] = CC[l][s][k][1] = 0.0;
+    }
+
+    const double *tb = ring + bc;     // this thread's pair in ring line 0 of input 0
+    const double *cur = tb, *prev = tb;
+    int q = 0;                        // stage of the current march step
+
+    // one march step; PH = step index mod 6 (compile time), t = step index
+    auto step = [&](auto ph, const int t) {
+        constexpr int PH = decltype(ph)::value;
+        const int R = jstart + t;     // grid line entering level 0
+        // ---- level 0 -------------------------------------------------------
+        {
+            double raw[NIN][2];
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) {
+                const double2 v = *reinterpret_cast<const double2 *>(cur + ((size_t)a * NR + PH) * BWP);
+                raw[a][0] = v.x;
+                raw[a][1] = v.y;
+            }
+            const bool out = outlane && R >= j0 && R < j1;
+            f.level0(out, (size_t)R * g.nx + gc, raw, U[0][PH % 3], CC[0][PH % 2], acc);
+        }
+        // ---- levels 1..L ---------------------------------------------------
+#pragma unroll
+        for (int l = 1; l <= L; ++l) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int sl_cu = (PH - l + 12) % 3;          // slot of line R-l in U[l-1]
+            const int sl_up = (PH - l - 1 + 12) % 3;      // line R-l-1
+            const int sl_dn = (PH - l + 1 + 12) % 3;      // line R-l+1
+            const int cs_in = (PH - l + 12) % 2;          // slot of line R-l in CC[l-1]
+            const int rho = R - l;
+            const double(&cu)[2] = U[l - 1][sl_cu];
+            const double(&up)[2] = U[l - 1][sl_up];
+            const double(&dn)[2] = U[l - 1][sl_dn];
+            double lf = __shfl_up_sync(0xffffffffu, cu[1], 1);
+            double rt = __shfl_down_sync(0xffffffffu, cu[0], 1);
+            double au[2];
+            au[0] = apply5c<OPK>(cu[0], lf, cu[1], dn[0], up[0], f.coef);
+            au[1] = apply5c<OPK>(cu[1], cu[0], rt, dn[1], up[1], f.coef);
+            // raw inputs of line R-l from the ring (previous hexad when PH < l)
+            const double *rb = (PH - l >= 0) ? cur + (size_t)(PH - l) * BWP : prev + (size_t)(6 + PH - l) * BWP;
+            auto rawget = [&](int a) -> double2 {
+                return *reinterpret_cast<const double2 *>(rb + (size_t)a * NR * BWP);
+            };
+            const bool out = outlane && rho >= j0 && rho < j1;
+            double un[2], cn[NC][2];
+            f.level(l, out, (size_t)rho * g.nx + gc, cu, au, CC[l - 1][cs_in], rawget, un, cn, acc);
+            if (l < L) {
+                const bool rowin = rho >= g.row_lo && rho < g.row_hi;
+                const bool m0 = rowin & colin0, m1 = rowin & colin1;
+                const int sl_new = (PH - l + 12) % 3;     // line R-l in U[l]
+                const int cs_new = (PH - l + 12) % 2;
+                U[l < L ? l : 0][sl_new][0] = m0 ? un[0] : 0.0;
+                U[l < L ? l : 0][sl_new][1] = m1 ? un[1] : 0.0;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    CC[l < L ? l : 0][cs_new][k][0] = cn[k][0];
+                    CC[l < L ? l : 0][cs_new][k][1] = cn[k][1];
+                }
+            }
+        }
+    };
+
+    // one stage boundary check + step, phase PH
+    auto phase = [&](auto ph, const int t) {
+        constexpr int PH = decltype(ph)::value;
+        if (t < T) {
+            if (PH % SR == 0) mbar_wait(&full[q % NST], (unsigned)((q / NST) & 1));
+            step(ph, t);
+            if (PH % SR == SR - 1) {
+                // this warp is done with stage q - RET (its lines are more than L behind the next step)
+                __syncwarp();
+                if (q >= RET) {
+                    const int qs = q - RET;
+                    if (lane == 0) mbar_arrive(&empty[qs % NST]);
+                    if (tid == 0 && qs + NST < nstg) {
+                        mbar_wait(&empty[qs % NST], (unsigned)((qs / NST) & 1));
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(qs + NST);
+                    }
+                }
+                ++q;
+            }
+        }
+    };
+
+    int hs = 0;   // ring line of the current hexad
+    for (int t0 = 0; t0 < T; t0 += 6) {
+        cur = tb + (size_t)hs * BWP;
+        prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
+        phase(std::integral_constant<int, 0>{}, t0 + 0);
+        phase(std::integral_constant<int, 1>{}, t0 + 1);
+        phase(std::integral_constant<int, 2>{}, t0 + 2);
+        phase(std::integral_constant<int, 3>{}, t0 + 3);
+        phase(std::integral_constant<int, 4>{}, t0 + 4);
+        phase(std::integral_constant<int, 5>{}, t0 + 5);
+        hs += 6;
+        if (hs == NR) hs = 0;
+    }
+
+    if (NRED > 0) {
+        __shared__ double sm[NR_ * (kChainThreads / 32)];
+        __shared__ int s_flag;
+        block_sum<NR_, kChainThreads>(acc, sm);
+        const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        grid_sum<NR_>(acc, rc, nb, bid, &s_flag);
+    }
+}
+
+// host: tensor map with an explicit box (kl_core.cu)
+int tmap_encode_box(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny, int box_x, int box_y);
+
+// lines per CTA: the redundant work is 2L / rows; keep it below ~10 % but leave >= ~3 CTAs per SM.
+template <int L>
+inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid) {
+    const long gx = (nx + ChainDims<L>::STRIP - 1) / ChainDims<L>::STRIP;
+    if (gx > kMaxBlocks) return false;
+    long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : 24 * L;
+    if (rows < 24) rows = 24;
+    const long want = (long)kNumSM * 4;
+    while (rows > 12 * L && rows > 16 && gx * ((ny + rows - 1) / rows) < want) rows -= 6;
+    if (rows > ny) rows = ny;
+    long gy = (ny + rows - 1) / rows;
+    if (gx * gy > kMaxBlocks) {
+        const long max_gy = kMaxBlocks / gx;
+        rows = (ny + max_gy - 1) / max_gy;
+        gy = (ny + rows - 1) / rows;
+    }
+    g->nx = nx; g->ny = ny; g->rows = (int)rows;
+    g->row_lo = 0; g->row_hi = ny;
+    *grid = dim3((unsigned)gx, (unsigned)gy);
+    return true;
+}
+
+// chain kernels need the TMA path: even nx, single GPU (a multi-GPU chain would need an L-line halo)
+inline bool chain_ok(const Ctx *c, int nx) { return c->opt_tma && c->opt_fuse && c->opt_chain && c->nranks == 1 && nx % 2 == 0 && nx >= 64; }
+
+template <class C, class Post>
+inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, const Post &post) {
+    constexpr int L = C::L;
+    using D = ChainDims<L>;
+    using RG = ChainRing<C::NIN, L>;
+    ChainGeo g;
+    dim3 grid;
+    if (!chain_geometry<L>(c, nx, ny, &g, &grid))
+        return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");
+    f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
+    RedCtl rc = redctl(c);
+    TMaps<C::NIN> tm;
+    for (int a = 0; a < C::NIN; ++a) KL_TRY(tmap_encode_box(c, &tm.m[a], f.in[a], nx, ny, D::BWP, RG::SR));
+    constexpr size_t smem = RG::bytes;
+#define KL_CH_LAUNCH(OPK)                                                                              \
+    {                                                                                                  \
+        static bool attr = false;                                                                      \
+        if (!attr) {                                                                                   \
+            cudaFuncSetAttribute(k_chain_tma<C, OPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr = true;                                                                               \
+        }                                                                                              \
+        k_chain_tma<C, OPK><<<grid, kChainThreads, smem, c->stream>>>(f, g, rc, tm);                   \
+    }
+    switch (op->kind) {
+        case KL_OP_POISSON5: KL_CH_LAUNCH(KL_OP_POISSON5) break;
+        case KL_OP_POISSON5_BRANCHY: KL_CH_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
+        case KL_OP_ANISO5: KL_CH_LAUNCH(KL_OP_ANISO5) break;
+        default: return c->fail(KL_ERR_INVALID, "launch_chain: not a built-in operator");
+    }
+#undef KL_CH_LAUNCH
+    c->stats.kernel_launches++;
+    // the post functor (scalar recurrences on the reduced sums) runs in its own one-warp kernel: the chain
+    // kernels are not templated on it (each instantiation is 6 phases x L levels of code)
+    if (C::NRED > 0 && !std::is_same<Post, NoPost>::value) {
+        k_post<Post><<<1, 32, 0, c->stream>>>(post, f.flags, f.step, f.run_on_conv);
+        c->stats.kernel_launches++;
+    }
+    return KL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// degree-L Chebyshev preconditioner in one pass (oracle/krylov_extras.c ko_cheb, Saad Alg. 12.1):
+//   level 0: u = r/theta, d = u ;  level l: d = fma(c1[l], d, c2[l]*(r - A u)) ; u = u + d ;  z = u_L
+// Same arithmetic per point as FChebStep (kl_ops.cuh) => bit-identical results.
+// mode 0: no reduction ; 1: acc0 = sum z*z ; 2: acc0 = sum r*z
+// ---------------------------------------------------------------------------
+template <int L_>
+struct ChCheb : ChainBase<1, L_, 1, 1> {
+    double *z, *d_out;     // d_out != nullptr: also store d_L (continuation with FChebStep for degrees > kChainMaxL)
+    int mode;
+    double theta;
+    double c1[L_], c2[L_];
+    FastDiv fd;
+    __device__ __forceinline__ void init() { fd.set(theta); }
+    __device__ __forceinline__ void level0(bool, size_t, const double (&raw)[1][2], double (&u)[2],
+                                           double (&cc)[1][2], double *) const {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            u[e] = fd.div(raw[0][e]);
+            cc[0][e] = u[e];
+        }
+    }
+    template <class RAW>
+    __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+                                          const double (&cin)[1][2], RAW raw, double (&u)[2], double (&cout)[1][2],
+                                          double *acc) const {
+        const double2 rr = raw(0);
+        const double r2[2] = {rr.x, rr.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double d = fma(c1[lv - 1], cin[0][e], c2[lv - 1] * (r2[e] - au[e]));
+            u[e] = up[e] + d;
+            cout[0][e] = d;
+        }
+        if (lv == L_ && out) {
+            stg2(z + idx, u[0], u[1]);
+            if (d_out) stg2(d_out + idx, cout[0][0], cout[0][1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (mode == 1) acc[0] = fma(u[e], u[e], acc[0]);
+                if (mode == 2) acc[0] = fma(r2[e], u[e], acc[0]);
+            }
+        }
+    }
+};
+
+}  // namespace kl

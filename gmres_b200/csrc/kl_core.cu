@@ -34,7 +34,7 @@ int ws_reserve(Ctx *c, size_t bytes) {
 int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     for (auto &e : c->tmaps)
-        if (e.base == base && e.nx == nx && e.ny == ny) {
+        if (e.base == base && e.nx == nx && e.ny == ny && e.k1 == 0 && e.k2 == 0) {
             memcpy(out, e.blob, sizeof(CUtensorMap));
             return KL_OK;
         }
@@ -57,6 +57,37 @@ int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
     if (c->tmaps.size() >= 256) c->tmaps.clear();
     Ctx::TmapEntry e;
     e.base = base; e.nx = nx; e.ny = ny;
+    memcpy(e.blob, out, sizeof(CUtensorMap));
+    c->tmaps.push_back(e);
+    return KL_OK;
+}
+
+// grid tensor map with an explicit box (chained stencil kernels, kl_chain_tma.cuh); key: k1 = box_x, k2 = box_y
+int tmap_encode_box(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny, int box_x, int box_y) {
+    for (auto &e : c->tmaps)
+        if (e.base == base && e.nx == nx && e.ny == ny && e.k1 == box_x && e.k2 == box_y) {
+            memcpy(out, e.blob, sizeof(CUtensorMap));
+            return KL_OK;
+        }
+    if (!c->encode_fn) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled entry point", e);
+        c->encode_fn = fn;
+    }
+    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
+    cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_x, (cuuint32_t)box_y};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled (box) failed");
+    if (c->tmaps.size() >= 256) c->tmaps.clear();
+    Ctx::TmapEntry e;
+    e.base = base; e.nx = nx; e.ny = ny; e.k1 = box_x; e.k2 = box_y;
     memcpy(e.blob, out, sizeof(CUtensorMap));
     c->tmaps.push_back(e);
     return KL_OK;
@@ -515,6 +546,8 @@ int kl_set_option(kl_handle_t h, int key, int value) {
         case KL_OPT_FUSE: h->opt_fuse = value != 0; break;
         case KL_OPT_PROFILE: h->opt_profile = value != 0; break;
         case KL_OPT_TMA: h->opt_tma = value != 0; break;
+        case KL_OPT_CHAIN: h->opt_chain = value != 0; break;
+        case KL_OPT_STENCIL_ROWS: h->opt_stencil_rows = value > 0 ? value : 0; break;
         case KL_OPT_REORTH_ETA:
             if (value < 1 || value > 1000) return KL_ERR_INVALID;
             h->opt_reorth_eta_permille = value;
@@ -541,6 +574,8 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_FUSE: *value = h->opt_fuse; break;
         case KL_OPT_PROFILE: *value = h->opt_profile; break;
         case KL_OPT_TMA: *value = h->opt_tma; break;
+        case KL_OPT_CHAIN: *value = h->opt_chain; break;
+        case KL_OPT_STENCIL_ROWS: *value = h->opt_stencil_rows; break;
         case KL_OPT_REORTH_ETA: *value = h->opt_reorth_eta_permille; break;
         case KL_OPT_PEER: *value = h->peer_ok ? 1 : 0; break;
         default: return KL_ERR_INVALID;

@@ -92,6 +92,7 @@ struct kl_context_s {
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_tma = 1;
+    int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
     // comm
@@ -542,8 +543,14 @@ struct NoPost {
 
 // post functor launched on its own (multi-GPU: after the all-reduce)
 template <class Post>
-__global__ void k_post(const Post post) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) post.run();
+__global__ void k_post(const Post post, const int *flags, const int step, const int run_on_conv) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (flags) {   // same gate as the kernel whose sums it consumes
+            const int ca = flags[I_CONV_AT];
+            if (!(ca < 0 || (run_on_conv && ca == step))) return;
+        }
+        post.run();
+    }
 }
 
 // ------------------------------------------------------------------------
@@ -565,10 +572,11 @@ inline int stencil_rows(int nx, int ny, int vec) {
 // after a reducing kernel: single GPU => post already ran fused; multi GPU =>
 // all-reduce the local sums and run the post functor in its own kernel.
 template <class Post>
-inline int finish_reduction(Ctx *c, int nred, const Post &post) {
+inline int finish_reduction(Ctx *c, int nred, const Post &post, const int *flags = nullptr, int step = 0,
+                            int run_on_conv = 0) {
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, c->d_S + S_RED, nred));
-        k_post<Post><<<1, 32, 0, c->stream>>>(post);
+        k_post<Post><<<1, 32, 0, c->stream>>>(post, flags, step, run_on_conv);
         c->stats.kernel_launches++;
     }
     return KL_OK;
@@ -650,7 +658,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
 #undef KL_ST_LAUNCH
 #undef KL_ST_GEO
     c->stats.kernel_launches++;
-    if (F::NRED > 0) return finish_reduction(c, F::NRED, post);
+    if (F::NRED > 0) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;
 }
 
@@ -671,7 +679,7 @@ inline int launch_pointwise(Ctx *c, F f, size_t n, const Post &post) {
     else
         k_pointwise<F, 1, Post><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
     c->stats.kernel_launches++;
-    if (F::NRED > 0) return finish_reduction(c, F::NRED, post);
+    if (F::NRED > 0) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;
 }
 

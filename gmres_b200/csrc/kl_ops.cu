@@ -168,6 +168,13 @@ int kl_apply_precond(kl_handle_t h, const kl_precond_t *M_inv, const kl_operator
     KL_TRY(prob_init(&P, c, A_x, M_inv, params, nparams, nx, ny));
     KL_TRY(ws_reserve(c, 4 * ws_need(P.n)));
     ws_reset(c);
+    if (c->pointer_mode == KL_POINTER_DEVICE && r != z) {
+        // device vectors are used in place (stream-ordered, returns after enqueue like kl_apply_operator)
+        double *aux = ws_take<double>(c, P.n), *aux2 = ws_take<double>(c, P.n);
+        KL_TRY(pc_apply(&P, r, z, aux, aux2, 0, false, NoPost{}));
+        KL_CUDA(c, cudaGetLastError());
+        return KL_OK;
+    }
     double *dr = ws_take<double>(c, P.n), *dz = ws_take<double>(c, P.n);
     double *aux = ws_take<double>(c, P.n), *aux2 = ws_take<double>(c, P.n);
     KL_TRY(stage_in(c, dr, r, P.n));
