@@ -45,6 +45,9 @@ WORKLOADS = {
                          aniso=(1.0, 0.01)),
     "gmres300": dict(solver="gmres_mgsr_omp", nx=300, ny=300, scaling="strong", pc="cbpr2", m=95),
     "cg4096": dict(solver="cg_omp", nx=4096, ny=4096, scaling="strong", pc=None, m=0),
+    # degree-4 Chebyshev (4 operator applications per preconditioner call, one HBM pass: kl_chain_tma.cuh)
+    "pcg8192cheb4": dict(solver="pcg_omp", nx=8192, ny=8192, scaling="strong", pc="cheb4", m=0),
+    "gmres4096cheb4": dict(solver="gmres_mgsr_omp", nx=4096, ny=4096, scaling="strong", pc="cheb4", m=95),
 }
 
 
@@ -113,7 +116,7 @@ class ClockSampler:
 
 def make_ops(kl, w):
     A = kl.aniso(*w["aniso"]) if w.get("aniso") else kl.stvec
-    M = kl.cbpr2 if w["pc"] == "cbpr2" else None
+    M = kl.cbpr2 if w["pc"] == "cbpr2" else (kl.cheb(int(w["pc"][4:])) if (w["pc"] or "").startswith("cheb") else None)
     return A, M
 
 

@@ -104,8 +104,8 @@ struct FBiS : StencilBase<2, (CB ? 0 : 2)> {
 // K1: p' = r + beta (p - omega ap) ; z1 = cbpr2(p') ; ap' = A z1 ; ap'.r0
 //     reads r,p,ap,r0  writes p',z1,ap'  (56n B instead of 40n + 24n)
 struct ChBiDir : ChainBase<3, 2, 1, 1> {
+    static constexpr int NSIDE = 1;     // side[0] = r0 (read only by the dot product of the last level)
     double *p_new, *z1, *ap_new;
-    const double *r0;
     const double *S;
     double beta, omega, d, calpha;
     FastDiv fd;
@@ -126,8 +126,8 @@ struct ChBiDir : ChainBase<3, 2, 1, 1> {
     }
     template <class RAW>
     __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
-                                          const double (&cin)[1][2], RAW, double (&u)[2], double (&cout)[1][2],
-                                          double *acc) const {
+                                          const double (&cin)[1][2], RAW, const double (&sd)[1][2], double (&u)[2],
+                                          double (&cout)[1][2], double *acc) const {
         if (lv == 1) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -139,10 +139,9 @@ struct ChBiDir : ChainBase<3, 2, 1, 1> {
             u[0] = u[1] = 0.0;
             cout[0][0] = cout[0][1] = 0.0;
             if (out) {
-                const double2 q = ldg2(r0 + idx);
                 stg2(ap_new + idx, au[0], au[1]);
-                acc[0] = fma(au[0], q.x, acc[0]);                                        // :126
-                acc[0] = fma(au[1], q.y, acc[0]);
+                acc[0] = fma(au[0], sd[0][0], acc[0]);                                   // :126 ap.r0
+                acc[0] = fma(au[1], sd[0][1], acc[0]);
             }
         }
     }
@@ -168,8 +167,8 @@ struct ChBiS : ChainBase<2, 2, 1, 2> {
     }
     template <class RAW>
     __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
-                                          const double (&cin)[1][2], RAW, double (&u)[2], double (&cout)[1][2],
-                                          double *acc) const {
+                                          const double (&cin)[1][2], RAW, const double (&)[1][2], double (&u)[2],
+                                          double (&cout)[1][2], double *acc) const {
         if (lv == 1) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -355,7 +354,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                     ChBiDir f;
                     for (int a = 0; a < 3; ++a) f.in[a] = v3[a];
                     set_gate(f, c, true);
-                    f.p_new = pnew; f.z1 = z1; f.ap_new = apnew; f.r0 = r0; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
+                    f.p_new = pnew; f.z1 = z1; f.ap_new = apnew; f.side[0] = r0; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
                     KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, PostBiAlpha{c->d_S}));
                     zz1 = z1;
                 } else if (cb) {
@@ -466,6 +465,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     KL_CUDA(c, cudaEventRecord(evB, c->stream));
     KL_CUDA(c, cudaStreamSynchronize(c->stream));
     KL_CUDA(c, cudaGetLastError());
+    prof_resolve(c);
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);

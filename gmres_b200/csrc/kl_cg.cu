@@ -4,10 +4,17 @@
 // All four share one device implementation (the serial and OpenMP variants
 // compute the same quantities; only their summation order differs).
 //
-// Per iteration (fused path, built-in operator):
+// Per iteration (fused path, built-in operator), 72n B for CG and 80n B for PCG + cbpr2:
+//   K1  x += alpha_prev*p ; p' = z + beta*p ; ax = A p' ; ax.p'   reads z,p,x  writes p',ax,x   48n B
+//   K2  r -= alpha ax ; r.r                                       reads r,ax   writes r         24n B
+//       (pcg + cbpr2: r' = r - alpha ax ; z = cbpr2(r') ; r'.r' ; r'.z in one stencil pass     32n B)
+// The x update of iteration k (cg.f90:127-129) is deferred into K1 of iteration k+1, which reads p anyway:
+// the same fma on the same operands, so x is bit-identical to the reference order, and one read of p per
+// iteration disappears (80n -> 72n).  The update still pending when the loop ends is flushed by one axpy.
+// Generic path (user operator, KL_OPT_FUSE = 0, preconditioners other than cbpr2):
 //   K1  p' = z + beta*p ; ax = A p' ; ax.p'         reads z,p   writes p',ax   32n B
 //   K2  x += alpha p' ; r -= alpha ax ; r.r          reads x,p',r,ax writes x,r 48n B
-//   K3  (pcg) z = cbpr2(r) ; r.z                     reads r     writes z       16n B
+//   K3  (pcg) z = M^-1 r ; r.z                       reads r     writes z       16n B
 // alpha, beta, ||r||, the convergence flag and the residual history live on the
 // device; the host polls once every KL_OPT_CHECK_EVERY iterations.
 #include <math.h>
@@ -48,11 +55,68 @@ struct PostCgEnd {
     }
 };
 
-// PCG with cbpr2: x += alpha p ; r' = r - alpha ax ; z = cbpr2(r') ; r'.r' ; r'.z in ONE stencil pass
-// (cg.f90:206-218).  in[0] = r, in[1] = ax ; r' goes to the other r buffer (neighbouring CTAs still read r).
-struct FPcgUpdate : StencilBase<2, 2> {
-    double *x, *r_new, *z;
-    const double *p;
+// K1 with the deferred x update: x += alpha_prev * p_old ; p_new = z + beta*p_old ; ax = A p_new ; ax.p_new
+// in[0] = z (r for plain CG), in[1] = p_old.  alpha_prev = S[S_ALPHA] of the previous iteration (0 before
+// the first one, where p_old = 0 as well).
+struct FCgDirX : StencilBase<2, 1> {
+    double *p_new, *ax, *x;
+    const double *S;
+    double beta, alpha_prev;
+    __device__ __forceinline__ void init() {
+        beta = S[S_BETA];
+        alpha_prev = S[S_ALPHA];
+    }
+    __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
+    template <int VEC>
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        double vx[VEC];
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(x + idx);
+            vx[0] = t.x; vx[VEC - 1] = t.y;
+        } else {
+            vx[0] = x[idx];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            vx[v] = fma(alpha_prev, raw[1][v], vx[v]);        // cg.f90:128 of the previous iteration
+            acc[0] = fma(au[v], cu[v], acc[0]);
+        }
+        KL_ST(VEC, x, idx, vx)
+        KL_ST(VEC, p_new, idx, cu)
+        KL_ST(VEC, ax, idx, au)
+    }
+};
+
+// K2 without x: r -= alpha ax ; acc0 = sum r*r     (cg.f90:130-133)
+struct PCgUpdateR : PwBase<1> {
+    double *r;
+    const double *ax;
+    const double *S;
+    double alpha;
+    __device__ __forceinline__ void init() { alpha = S[S_ALPHA]; }
+    template <int VEC>
+    __device__ __forceinline__ void elem(size_t i, double *acc) const {
+        double vr[VEC], va[VEC];
+        KL_LD(VEC, va, ax, i)
+        if (VEC == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(r + i);
+            vr[0] = t.x; vr[VEC - 1] = t.y;
+        } else {
+            vr[0] = r[i];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            vr[v] = fma(-alpha, va[v], vr[v]);
+            acc[0] = fma(vr[v], vr[v], acc[0]);
+        }
+        KL_ST(VEC, r, i, vr)
+    }
+};
+
+// PCG + cbpr2 without x: r' = r - alpha ax ; z = cbpr2(r') ; r'.r' ; r'.z   (cg.f90:209-218)
+struct FPcgUpdateR : StencilBase<2, 2> {
+    double *r_new, *z;
     const double *S;
     double alpha, d, calpha;
     FastDiv fd;
@@ -64,23 +128,14 @@ struct FPcgUpdate : StencilBase<2, 2> {
     template <int VEC>
     __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
                                           const double (&au)[VEC], double *acc) const {
-        double vx[VEC], vp[VEC], rn[VEC], zz[VEC];
-        KL_LD(VEC, vp, p, idx)
-        if (VEC == 2) {
-            double2 t = *reinterpret_cast<const double2 *>(x + idx);
-            vx[0] = t.x; vx[VEC - 1] = t.y;
-        } else {
-            vx[0] = x[idx];
-        }
+        double rn[VEC], zz[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            vx[v] = fma(alpha, vp[v], vx[v]);                 // :208
             rn[v] = fma(-alpha, raw[1][v], raw[0][v]);        // :209
             zz[v] = fma(calpha, rn[v] - au[v], cu[v]);        // chebyshev.f90:35
             acc[0] = fma(rn[v], rn[v], acc[0]);               // :210
             acc[1] = fma(rn[v], zz[v], acc[1]);               // :216
         }
-        KL_ST(VEC, x, idx, vx)
         KL_ST(VEC, r_new, idx, rn)
         KL_ST(VEC, z, idx, zz)
     }
@@ -104,7 +159,8 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
-    const bool fuse_pc = fused && P.pc.kind == KL_PC_CBPR2;   // update + cbpr2 in one pass (88n B/iteration)
+    const bool fuse_pc = fused && P.pc.kind == KL_PC_CBPR2;   // update + cbpr2 in one pass
+    const bool defer_x = fused && (!prec || fuse_pc);         // x update folded into the next K1 (72n / 80n B)
     const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0) + (fuse_pc ? 1 : 0);
     KL_TRY(ws_reserve(c, nvec * ws_need(n)));
     ws_reset(c);
@@ -151,7 +207,17 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
         if (batch > maxit - done) batch = maxit - done;
         for (int k = 0; k < batch; ++k) {
             // ---- K1
-            if (fused) {
+            if (defer_x) {
+                ProfScope ps(c, 0, "cg_xdir_apply_dot (stencil: x+=alpha_prev*p; p=z+beta*p; ax=A p; ax.p)", 48.0 * n);
+                Halo H;
+                const double *vecs[2] = {z, pold};
+                KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                FCgDirX f;
+                set_io(f, &P, vecs, H);
+                set_gate(f, c, true);
+                f.p_new = pnew; f.ax = ax; f.x = dx; f.S = c->d_S;
+                KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgAlpha{c->d_S}));
+            } else if (fused) {
                 ProfScope ps(c, 0, "cg_dir_apply_dot (stencil: p=z+beta*p; ax=A p; ax.p)", 32.0 * n);
                 Halo H;
                 const double *vecs[2] = {z, pold};
@@ -174,16 +240,25 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
             }
             // ---- K2 (+K3 fused for cbpr2)
             if (fuse_pc) {
-                ProfScope ps(c, 3, "pcg_update_precond (stencil: x+=alpha p; r-=alpha ax; z=cbpr2(r); r.r; r.z)", 56.0 * n);
+                ProfScope ps(c, 3, "pcg_rupdate_precond (stencil: r-=alpha ax; z=cbpr2(r); r.r; r.z)", 32.0 * n);
                 Halo H;
                 const double *vecs[2] = {r, ax};
                 KL_TRY(halo_exchange(&P, vecs, 2, &H));
-                FPcgUpdate f;
+                FPcgUpdateR f;
                 set_io(f, &P, vecs, H);
                 set_gate(f, c, true);
-                f.x = dx; f.r_new = r_alt; f.z = z; f.p = pnew; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
+                f.r_new = r_alt; f.z = z; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
                 KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 2}));
                 std::swap(r, r_alt);
+                double *t = pold; pold = pnew; pnew = t;
+                continue;
+            }
+            if (defer_x) {
+                ProfScope ps(c, 1, "cg_update_r_dot (pointwise: r-=alpha ax; r.r)", 24.0 * n);
+                PCgUpdateR u;
+                set_gate(u, c, true);
+                u.r = r; u.ax = ax; u.S = c->d_S;
+                KL_TRY(launch_pointwise(c, u, n, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}));
                 double *t = pold; pold = pnew; pnew = t;
                 continue;
             }
@@ -211,6 +286,19 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
             break;
         }
     }
+    if (defer_x) {
+        // flush the pending x += alpha p of the last executed iteration (kernels after the convergence step
+        // were gated off, so S_ALPHA and the p buffer of that iteration are intact).  Iteration i wrote its
+        // direction into p1 for odd i and into p0 for even i.
+        if (status == KL_NOT_CONVERGED) KL_TRY(read_back(c));
+        const int its_done = c->h_pinned_i[I_ITER];
+        if (its_done > 0) {
+            PAxpy u;
+            set_gate(u, c, false);
+            u.a = dx; u.b = (its_done & 1) ? p1 : p0; u.y = dx; u.S = c->d_S; u.s_idx = S_ALPHA; u.sign = 1.0;
+            KL_TRY(launch_pointwise(c, u, n, NoPost{}));
+        }
+    }
     KL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     KL_TRY(stage_out(c, x, dx, n));
     KL_TRY(fetch_history(c));
@@ -228,7 +316,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     c->stats.cycles = polls;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
-    c->stats.algorithmic_bytes = (double)its * (fuse_pc ? 88.0 : (prec ? 96.0 : 80.0)) * (double)n;
+    c->stats.algorithmic_bytes = (double)its * (fuse_pc ? 80.0 : (prec ? 96.0 : (defer_x ? 72.0 : 80.0))) * (double)n;
     *res_out = c->h_pinned[S_RES];
     if (status == KL_OK) *iter = c->h_pinned_i[I_CONV_AT];   // count on exit; unchanged if not converged
     return status;

@@ -36,8 +36,11 @@
 //        `out`: the points are in the CTA's output range (store level-0 outputs)
 //   template <class RAW>
 //   void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
-//              const double (&cin)[NC][2], RAW raw, double (&u)[2], double (&cout)[NC][2], double *acc)
-//        lv in 1..L ; up = field of level lv-1, au = A up ; raw(a) = double2 of input a at this line
+//              const double (&cin)[NC][2], RAW raw, const double (&sd)[max(NSIDE,1)][2], double (&u)[2],
+//              double (&cout)[NC][2], double *acc)
+//        lv in 1..L ; up = field of level lv-1, au = A up ; raw(a) = double2 of input a at this line ;
+//        sd = side inputs (arrays side[0..NSIDE), read point-wise at the last level's output points only,
+//        valid for lv == L && out; the kernel prefetches them two lines ahead into registers)
 // level0 must map all-zero inputs to u = 0 (outside the domain TMA delivers zeros).
 #pragma once
 #include <type_traits>
@@ -58,15 +61,19 @@ struct ChainDims {
     static constexpr int BW = STRIP + 2 * H;            // columns a CTA needs
     static constexpr int BWP = (BW + 15) & ~15;         // TMA box width (row pitch multiple of 128 B)
 };
-template <int NIN, int L>
+// Ring geometry: SR lines per stage, NST stages (defaults in ChainBase, a functor may override them).  The
+// ring holds NR = SR*NST lines (a multiple of 6: the march is unrolled by hexads) and keeps RET stages alive
+// behind the current one so that level l can re-read raw inputs l lines back.
+template <class C>
 struct ChainRing {
-    static constexpr int SR = (NIN == 1) ? 6 : 2;       // lines per stage
-    static constexpr int NST = (NIN == 1) ? 4 : 6;      // stages
-    static constexpr int NR = SR * NST;                 // ring lines (multiple of 6)
-    static constexpr int RET = (L + SR - 1) / SR;       // stages kept alive behind the current one
+    static constexpr int SR = C::SR;
+    static constexpr int NST = C::NST;
+    static constexpr int NR = SR * NST;
+    static constexpr int RET = (C::L + SR - 1) / SR;
+    static_assert(6 % SR == 0, "a hexad must hold whole stages");
     static_assert(NR % 6 == 0, "ring must hold whole hexads");
     static_assert(NST - RET >= 2, "ring too shallow");
-    static constexpr size_t bytes = (size_t)NIN * NR * ChainDims<L>::BWP * sizeof(double) + 2 * NST * 8 + 64;
+    static constexpr size_t bytes = (size_t)C::NIN * NR * ChainDims<C::L>::BWP * sizeof(double) + 2 * NST * 8 + 64;
 };
 
 struct ChainGeo {
@@ -80,8 +87,15 @@ struct ChainBase {
     static constexpr int L = L_;
     static constexpr int NC = NC_;
     static constexpr int NRED = NRED_;
+    static constexpr int NSIDE = 0;     // point-wise side inputs of the last level, prefetched 2 lines ahead
+    // ring: 1 input: 3-line stages, 18 / 24 lines ; more inputs: 1-line stages, 6 lines (a CTA needs ~2 us per
+    // line, so three lines of lookahead cover the DRAM latency; small rings buy 6 CTAs per SM instead)
+    static constexpr int SR = NIN_ == 1 ? 3 : 1;
+    static constexpr int NST = NIN_ == 1 ? (L_ <= 2 ? 6 : 8) : 6;
+    static constexpr int MINB = L_ <= 2 ? 6 : (L_ <= 4 ? 4 : 3);   // CTAs per SM the register budget is cut for
     static_assert(L_ >= 1 && L_ <= kChainMaxL, "chain length");
     const double *in[NIN_];
+    const double *side[1];
     const int *flags;
     int step;
     int run_on_conv;
@@ -113,7 +127,7 @@ __device__ __forceinline__ double apply5c(double c, double l, double r, double d
 }
 
 template <class C, int OPK>
-__global__ void __launch_bounds__(kChainThreads)
+__global__ void __launch_bounds__(kChainThreads, C::MINB)
 k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_constant__ TMaps<C::NIN> tm) {
     if (c_in.skip()) return;
     C f = c_in;
@@ -121,7 +135,8 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     constexpr int NIN = C::NIN, L = C::L, NC = C::NC, NRED = C::NRED;
     constexpr int NR_ = NRED > 0 ? NRED : 1;
     using D = ChainDims<L>;
-    using RG = ChainRing<NIN, L>;
+    using RG = ChainRing<C>;
+    constexpr int NSIDE = C::NSIDE, NSD = NSIDE > 0 ? NSIDE : 1;
     constexpr int H = D::H, WW = D::WW, BWP = D::BWP;
     constexpr int SR = RG::SR, NST = RG::NST, NR = RG::NR, RET = RG::RET;
     constexpr unsigned kStageBytes = NIN * SR * BWP * sizeof(double);
@@ -178,6 +193,12 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             for (int k = 0; k < NC; ++k) CC[l][s][k][0] = CC[l][s][k][1] = 0.0;
     }
 
+    double SD[NSD][3][2];             // side inputs of the last level: lines rho, rho+1, rho+2
+#pragma unroll
+    for (int a = 0; a < NSD; ++a)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) SD[a][s][0] = SD[a][s][1] = 0.0;
+
     const double *tb = ring + bc;     // this thread's pair in ring line 0 of input 0
     const double *cur = tb, *prev = tb;
     int q = 0;                        // stage of the current march step
@@ -186,6 +207,18 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     auto step = [&](auto ph, const int t) {
         constexpr int PH = decltype(ph)::value;
         const int R = jstart + t;     // grid line entering level 0
+        if (NSIDE > 0) {
+            // the last level reaches line R - L + 2 two steps from now: start its point-wise loads today
+            const int rho2 = R - L + 2;
+            if (outlane && rho2 >= j0 && rho2 < j1) {
+#pragma unroll
+                for (int a = 0; a < NSIDE; ++a) {
+                    const double2 v = ldg2(f.side[a] + (size_t)rho2 * g.nx + gc);
+                    SD[a][(PH + 2) % 3][0] = v.x;
+                    SD[a][(PH + 2) % 3][1] = v.y;
+                }
+            }
+        }
         // ---- level 0 -------------------------------------------------------
         {
             double raw[NIN][2];
@@ -223,7 +256,13 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             };
             const bool out = outlane && rho >= j0 && rho < j1;
             double un[2], cn[NC][2];
-            f.level(l, out, (size_t)rho * g.nx + gc, cu, au, CC[l - 1][cs_in], rawget, un, cn, acc);
+            double sd[NSD][2];
+#pragma unroll
+            for (int a = 0; a < NSD; ++a) {
+                sd[a][0] = SD[a][PH % 3][0];
+                sd[a][1] = SD[a][PH % 3][1];
+            }
+            f.level(l, out, (size_t)rho * g.nx + gc, cu, au, CC[l - 1][cs_in], rawget, sd, un, cn, acc);
             if (l < L) {
                 const bool rowin = rho >= g.row_lo && rho < g.row_hi;
                 const bool m0 = rowin & colin0, m1 = rowin & colin1;
@@ -318,7 +357,7 @@ template <class C, class Post>
 inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, const Post &post) {
     constexpr int L = C::L;
     using D = ChainDims<L>;
-    using RG = ChainRing<C::NIN, L>;
+    using RG = ChainRing<C>;
     ChainGeo g;
     dim3 grid;
     if (!chain_geometry<L>(c, nx, ny, &g, &grid))
@@ -378,8 +417,8 @@ struct ChCheb : ChainBase<1, L_, 1, 1> {
     }
     template <class RAW>
     __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
-                                          const double (&cin)[1][2], RAW raw, double (&u)[2], double (&cout)[1][2],
-                                          double *acc) const {
+                                          const double (&cin)[1][2], RAW raw, const double (&)[1][2], double (&u)[2],
+                                          double (&cout)[1][2], double *acc) const {
         const double2 rr = raw(0);
         const double r2[2] = {rr.x, rr.y};
 #pragma unroll
