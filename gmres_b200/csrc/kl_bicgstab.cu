@@ -292,7 +292,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     const bool prec = P.pc.kind != KL_PC_NONE;
     const bool cb = P.pc.kind == KL_PC_CBPR2;
     const bool fused = c->opt_fuse && P.builtin_op() && (!prec || cb);
-    const bool chain = fused && cb && chain_ok(c, P.nx);   // cbpr2 and the operator in one pass (160n B/iteration)
+    const bool chain = fused && cb && chain_ok(&P, 2);   // cbpr2 and the operator in one pass (160n B/iteration)
     const size_t n = P.n;
     const int maxit = *iter;
     c->stats = kl_stats_t{};
@@ -348,11 +348,12 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
             if (fused) {
                 Halo H;
                 const double *v3[3] = {r, pold, apold};
-                KL_TRY(halo_exchange(&P, v3, 3, &H));
+                if (chain) KL_TRY(halo_exchange_lines(&P, v3, 3, 2, &H));
+                else KL_TRY(halo_exchange(&P, v3, 3, &H));
                 if (cb && chain) {
                     ProfScope ps(c, 0, "bicg_dir_cbpr2_apply_dot (chain: p'=r+beta(p-omega ap); z1=cbpr2(p'); ap'=A z1; ap'.r0)", 56.0 * n);
                     ChBiDir f;
-                    for (int a = 0; a < 3; ++a) f.in[a] = v3[a];
+                    set_io(f, &P, v3, H);
                     set_gate(f, c, true);
                     f.p_new = pnew; f.z1 = z1; f.ap_new = apnew; f.side[0] = r0; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
                     KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, PostBiAlpha{c->d_S}));
@@ -380,11 +381,12 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
                     zz1 = pnew;
                 }
                 const double *v2[2] = {r, apnew};
-                KL_TRY(halo_exchange(&P, v2, 2, &H));
+                if (chain) KL_TRY(halo_exchange_lines(&P, v2, 2, 2, &H));
+                else KL_TRY(halo_exchange(&P, v2, 2, &H));
                 if (cb && chain) {
                     ProfScope ps(c, 1, "bicg_s_cbpr2_apply_dots (chain: s=r-alpha ap'; z2=cbpr2(s); as=A z2; as.s; as.as)", 40.0 * n);
                     ChBiS f;
-                    for (int a = 0; a < 2; ++a) f.in[a] = v2[a];
+                    set_io(f, &P, v2, H);
                     set_gate(f, c, true);
                     f.s = s; f.z2 = z2; f.as = as; f.S = c->d_S; f.d = cf.d; f.calpha = cf.alpha;
                     KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, PostBiOmega{c->d_S}));

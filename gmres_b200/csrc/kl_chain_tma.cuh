@@ -95,6 +95,8 @@ struct ChainBase {
     static constexpr int MINB = L_ <= 2 ? 6 : (L_ <= 4 ? 4 : 3);   // CTAs per SM the register budget is cut for
     static_assert(L_ >= 1 && L_ <= kChainMaxL, "chain length");
     const double *in[NIN_];
+    const double *lo[NIN_];     // multi-GPU: the neighbours' L boundary lines of every input (nullptr at the
+    const double *hi[NIN_];     // global boundary): lo = grid lines -L..-1, hi = lines ny..ny+L-1
     const double *side[1];
     const int *flags;
     int step;
@@ -222,11 +224,24 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         // ---- level 0 -------------------------------------------------------
         {
             double raw[NIN][2];
+            if ((R < 0 && f.lo[0] != nullptr) || (R >= g.ny && f.hi[0] != nullptr)) {
+                // multi-GPU: this line belongs to a neighbour rank; TMA delivered zeros, take it from the halo
+                // buffer and patch the ring (every thread re-reads only its own column pair later)
 #pragma unroll
-            for (int a = 0; a < NIN; ++a) {
-                const double2 v = *reinterpret_cast<const double2 *>(cur + ((size_t)a * NR + PH) * BWP);
-                raw[a][0] = v.x;
-                raw[a][1] = v.y;
+                for (int a = 0; a < NIN; ++a) {
+                    const double *src = R < 0 ? f.lo[a] + (size_t)(R + L) * g.nx : f.hi[a] + (size_t)(R - g.ny) * g.nx;
+                    raw[a][0] = colin0 ? __ldg(src + gc) : 0.0;
+                    raw[a][1] = colin1 ? __ldg(src + gc + 1) : 0.0;
+                    *reinterpret_cast<double2 *>(const_cast<double *>(cur) + ((size_t)a * NR + PH) * BWP) =
+                        make_double2(raw[a][0], raw[a][1]);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) {
+                    const double2 v = *reinterpret_cast<const double2 *>(cur + ((size_t)a * NR + PH) * BWP);
+                    raw[a][0] = v.x;
+                    raw[a][1] = v.y;
+                }
             }
             const bool out = outlane && R >= j0 && R < j1;
             f.level0(out, (size_t)R * g.nx + gc, raw, U[0][PH % 3], CC[0][PH % 2], acc);
@@ -350,9 +365,6 @@ inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid) {
     return true;
 }
 
-// chain kernels need the TMA path: even nx, single GPU (a multi-GPU chain would need an L-line halo)
-inline bool chain_ok(const Ctx *c, int nx) { return c->opt_tma && c->opt_fuse && c->opt_chain && c->nranks == 1 && nx % 2 == 0 && nx >= 64; }
-
 template <class C, class Post>
 inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, const Post &post) {
     constexpr int L = C::L;
@@ -362,6 +374,9 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     dim3 grid;
     if (!chain_geometry<L>(c, nx, ny, &g, &grid))
         return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");
+    // lines of the neighbour ranks are unknowns too (recomputed redundantly level by level)
+    if (f.lo[0]) g.row_lo = -L;
+    if (f.hi[0]) g.row_hi = ny + L;
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
     TMaps<C::NIN> tm;
@@ -387,6 +402,7 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     // the post functor (scalar recurrences on the reduced sums) runs in its own one-warp kernel: the chain
     // kernels are not templated on it (each instantiation is 6 phases x L levels of code)
     if (C::NRED > 0 && !std::is_same<Post, NoPost>::value) {
+        if (c->nranks > 1) return finish_reduction(c, C::NRED, post, f.flags, f.step, f.run_on_conv);
         k_post<Post><<<1, 32, 0, c->stream>>>(post, f.flags, f.step, f.run_on_conv);
         c->stats.kernel_launches++;
     }

@@ -32,7 +32,7 @@ int prob_init(Prob *P, Ctx *c, const kl_operator_t *op, const kl_precond_t *pc, 
     P->n = (size_t)nx * P->nyl;
     KL_CUDA(c, cudaSetDevice(c->device));
     if (c->nranks > 1) {
-        size_t need = (size_t)nx * 8;  // 4 slots x {lo,hi}
+        size_t need = (size_t)nx * 8 * kChainMaxL;  // 4 slots x {lo,hi} x up to kChainMaxL lines (chained kernels)
         if (c->halo_doubles < need) {
             cudaStreamSynchronize(c->stream);
             cudaFree(c->d_halo);
@@ -57,6 +57,21 @@ int halo_exchange(Prob *P, const double *const *vecs, int nvec, Halo *H) {
     }
     // NOTE: a stencil kernel treats lo[0]==nullptr as "no lower neighbour" for all inputs.
     return comm_halo_exchange(c, slo, shi, H->lo, H->hi, nvec, P->nx);
+}
+
+// L-line halo for the temporally blocked kernels: lo = the lower neighbour's last `nlines` lines (grid lines
+// -nlines..-1 in order), hi = the upper neighbour's first `nlines` lines.  Needs nyl >= nlines on every rank.
+int halo_exchange_lines(Prob *P, const double *const *vecs, int nvec, int nlines, Halo *H) {
+    Ctx *c = P->c;
+    for (int a = 0; a < 4; ++a) H->lo[a] = H->hi[a] = nullptr;
+    if (c->nranks == 1) return KL_OK;
+    if (nvec > 4 || nlines < 1 || nlines > P->nyl) return c->fail(KL_ERR_INVALID, "halo_exchange_lines: bad arguments");
+    const double *slo[4], *shi[4];
+    for (int a = 0; a < nvec; ++a) {
+        slo[a] = vecs[a];
+        shi[a] = vecs[a] + (size_t)(P->nyl - nlines) * P->nx;
+    }
+    return comm_halo_exchange(c, slo, shi, H->lo, H->hi, nvec, nlines * P->nx);
 }
 
 int op_apply(Prob *P, const double *x, double *y, bool gated) {

@@ -29,6 +29,15 @@ struct Halo {
 // boundary / single GPU).
 int halo_exchange(Prob *P, const double *const *vecs, int nvec, Halo *H);
 
+int halo_exchange_lines(Prob *P, const double *const *vecs, int nvec, int nlines, Halo *H);
+// can the temporally blocked kernels run L levels on this problem?  (all ranks take the same decision)
+inline bool chain_ok(const Prob *P, int L) {
+    const Ctx *c = P->c;
+    if (!(c->opt_tma && c->opt_fuse && c->opt_chain) || P->nx % 2 != 0 || P->nx < 64) return false;
+    if (c->nranks == 1) return true;
+    return P->ny / c->nranks >= L && (size_t)L * P->nx <= 65536;   // L-line halo fits the exchange buffers
+}
+
 template <class F>
 inline void set_io(F &f, const Prob *P, const double *const *vecs, const Halo &H) {
     for (int a = 0; a < F::NIN; ++a) {
@@ -146,9 +155,12 @@ int pc_apply(Prob *P, const double *r, double *z, double *aux, double *aux2, int
         int s0 = 0;
         // ping-pong so that the final result lands in z: z_k = z if k odd else aux
         double *zb[2] = {z, aux};
-        if (chain_ok(c, P->nx)) {
+        const int kc = k < kChainMaxL ? k : kChainMaxL;
+        if (chain_ok(P, kc)) {
             // the first min(k, 6) steps in ONE pass over r (kl_chain_tma.cuh): 16n B instead of 40n B per step
-            const int kc = k < kChainMaxL ? k : kChainMaxL;
+            Halo H;
+            const double *hv[1] = {r};
+            KL_TRY(halo_exchange_lines(P, hv, 1, kc, &H));
             double c1s[kChainMaxL], c2s[kChainMaxL];
             for (int s = 0; s < kc; ++s) {
                 double rho = 1.0 / (2.0 * sigma - rho_prev);
@@ -160,7 +172,7 @@ int pc_apply(Prob *P, const double *r, double *z, double *aux, double *aux2, int
 #define KL_CC(LL)                                                                       \
     case LL: {                                                                          \
         ChCheb<LL> f;                                                                   \
-        f.in[0] = r;                                                                    \
+        set_io(f, P, hv, H);                                                            \
         set_gate(f, c, gated);                                                          \
         f.z = dst; f.d_out = (kc == k) ? nullptr : aux2; f.mode = (kc == k) ? mode : 0; \
         f.theta = theta;                                                                \

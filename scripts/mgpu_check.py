@@ -39,6 +39,9 @@ for (nx, ny) in ((512, 512), (300, 301), (1000, 64)):
         check(f"apply {nx}x{ny} kind={A.kind}", np.array_equal(y, h1.apply(A, xg, nx, ny)))
     z = gather(h.apply_precond(kl.cbpr2, kl.stvec, xl, P, nx, ny), nx, ny)
     check(f"cbpr2 {nx}x{ny}", np.array_equal(z, h1.apply_precond(kl.cbpr2, kl.stvec, xg, P, nx, ny)))
+    for k in (2, 3, 6, 7):   # temporally blocked Chebyshev with a k-line halo (k <= 6 in one pass)
+        zc = gather(h.apply_precond(kl.cheb(k), kl.stvec, xl, (0.2, 8.2), nx, ny), nx, ny)
+        check(f"cheb({k}) chain {nx}x{ny}", np.array_equal(zc, h1.apply_precond(kl.cheb(k), kl.stvec, xg, (0.2, 8.2), nx, ny)))
     bg = h1.apply(kl.stvec, np.ones(nx * ny), nx, ny)
     bl = bg.reshape(ny, nx)[j0:j0 + nyl].reshape(-1).copy()
     for name, run in (
