@@ -160,6 +160,35 @@ module krylov_b200_c
             integer(c_int), value :: np
             integer(c_int) :: rc
         end function
+        function kl_gmres_mgsr_dense(h, A, n, b, x, m, tol, final_err, v_err, n_out, restart_out) &
+                bind(C, name="kl_gmres_mgsr_dense") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: A(*), b(*)
+            integer(c_int), value :: n, m
+            real(c_double), intent(out) :: x(*), final_err(*), v_err(*)
+            real(c_double), value :: tol
+            integer(c_int), intent(out) :: n_out, restart_out
+            integer(c_int) :: rc
+        end function
+        function kl_gmres_hh_dense(h, A, n, b, x, m, tol, final_err, v_err, n_out, stages_out) &
+                bind(C, name="kl_gmres_hh_dense") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: A(*), b(*)
+            integer(c_int), value :: n, m
+            real(c_double), intent(out) :: x(*), final_err(*), v_err(*)
+            real(c_double), value :: tol
+            integer(c_int), intent(out) :: n_out, stages_out
+            integer(c_int) :: rc
+        end function
+        function kl_generate_matrix(h, Hm, n) bind(C, name="kl_generate_matrix") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: Hm(*)
+            integer(c_int), value :: n
+            integer(c_int) :: rc
+        end function
     end interface
 
 contains
@@ -217,7 +246,7 @@ MODULE GMRES_MGSR_MOD                      ! replaces src/gmres_mgsr.f90
     use krylov_b200_c
     implicit none
     private
-    public :: gmres_mgsr_omp, gmres_mgsr_mf
+    public :: gmres_mgsr_omp, gmres_mgsr_mf, gmres_mgsr_dense
 CONTAINS
     subroutine gmres_mgsr_omp(Ax_vec, b, x, m, tol, final_err, v_err, n_out, restart_out, M_inv, params)
         procedure(stencil_vector) :: Ax_vec
@@ -260,6 +289,20 @@ CONTAINS
                               restart_out, pc, params, int(size(params), c_int))
         if (rc < 0) error stop "krylov_b200: kl_gmres_mgsr_mf failed"
     end subroutine
+
+    subroutine gmres_mgsr_dense(A, b, x, m, tol, final_err, v_err, n_out, restart_out)   ! gmres_mgsr.f90:11
+        real(8), intent(in) :: A(:,:), b(:)
+        real(8), allocatable, intent(out) :: x(:)
+        integer, intent(in) :: m
+        real(8), intent(in) :: tol
+        real(8), allocatable, intent(out) :: final_err(:), v_err(:)
+        integer, intent(out) :: n_out, restart_out
+        integer(c_int) :: rc
+        allocate(x(size(b)), final_err(m), v_err(m + 1))      ! gmres_mgsr.f90:27
+        rc = kl_gmres_mgsr_dense(the_handle(), A, int(size(A, 1), c_int), b, x, int(m, c_int), tol, final_err, v_err, &
+                                 n_out, restart_out)
+        if (rc < 0) error stop "krylov_b200: kl_gmres_mgsr_dense failed"
+    end subroutine
 END MODULE GMRES_MGSR_MOD
 
 
@@ -268,7 +311,7 @@ MODULE gmres_hh_mod                        ! replaces src/gmres_hh.f90
     use krylov_b200_c
     implicit none
     private
-    public :: gmres_hh_omp, gmres_hh_prec_omp
+    public :: gmres_hh_omp, gmres_hh_prec_omp, gmres_hh_dense
 CONTAINS
     subroutine gmres_hh_omp(Ax_vec, b, x, m, tol, final_err, v_err, n_out, stages_out)
         procedure(stencil_vector) :: Ax_vec
@@ -307,7 +350,38 @@ CONTAINS
                                   stages_out, pc, params, int(size(params), c_int))
         if (rc < 0) error stop "krylov_b200: kl_gmres_hh_prec_omp failed"
     end subroutine
+
+    subroutine gmres_hh_dense(A, b, x, m, tol, final_err, v_err, n_out, stages_out)      ! gmres_hh.f90:10
+        real(8), intent(in) :: A(:,:), b(:)
+        real(8), allocatable, intent(out) :: x(:)
+        integer, intent(in) :: m
+        real(8), intent(in) :: tol
+        real(8), allocatable, intent(out) :: final_err(:), v_err(:)
+        integer, intent(out) :: n_out, stages_out
+        integer(c_int) :: rc
+        allocate(x(size(b)), final_err(m), v_err(m + 1))      ! gmres_hh.f90:28-30
+        rc = kl_gmres_hh_dense(the_handle(), A, int(size(A, 1), c_int), b, x, int(m, c_int), tol, final_err, v_err, &
+                               n_out, stages_out)
+        if (rc < 0) error stop "krylov_b200: kl_gmres_hh_dense failed"
+    end subroutine
 END MODULE gmres_hh_mod
+
+
+MODULE hilbert                             ! replaces src/problems/hilbert.f90
+    use krylov_b200_c
+    implicit none
+    private
+    public :: generate_matrix
+CONTAINS
+    subroutine generate_matrix(H, n)
+        real(8), allocatable, intent(out) :: H(:,:)
+        integer, intent(in) :: n
+        integer(c_int) :: rc
+        allocate(H(n, n))                                     ! hilbert.f90:11
+        rc = kl_generate_matrix(the_handle(), H, int(n, c_int))
+        if (rc < 0) error stop "krylov_b200: kl_generate_matrix failed"
+    end subroutine
+END MODULE hilbert
 
 
 MODULE conjugate_gradient                  ! replaces src/cg.f90

@@ -115,6 +115,11 @@ def load_library():
         getattr(L, name).argtypes = cg
     for name in ("kl_pcg", "kl_pcg_omp", "kl_pbicgstab", "kl_pbicgstab_omp"):
         getattr(L, name).argtypes = cg + pc
+    dn = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, _dp, _dp, _ip, _ip]
+    L.kl_gmres_mgsr_dense.argtypes = dn
+    L.kl_gmres_hh_dense.argtypes = dn
+    L.kl_generate_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.kl_dense_matvec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.kl_lanczos.argtypes = [C.c_void_p, C.POINTER(kl_operator_t), C.c_int, C.c_int, C.c_int, _dp, _dp]
     L.kl_cheb_params_from_ritz.argtypes = [C.c_double, C.c_double, _dp]
     L.kl_get_history.argtypes = [C.c_void_p, _dp, C.c_int, _ip]
@@ -390,6 +395,52 @@ class Handle:
 
     def gmres_hh_prec_omp(self, Ax_vec, b, m, tol, m_inv=None, params=None, nx=None, ny=None):
         return self._gmres(self._L.kl_gmres_hh_prec_omp, Ax_vec, b, m, tol, m_inv, params, nx, ny)
+
+    # -- dense-operator variants (src/gmres_mgsr.f90:11, src/gmres_hh.f90:10, src/problems/hilbert.f90:6)
+    def _dense_in(self, A, n):
+        """A(n,n) as the Fortran array.  numpy: any layout (copied to column-major); CUDA tensor: its memory
+        must already be column-major (pass A.t().contiguous() of a row-major torch matrix)."""
+        if _is_torch_cuda(A):
+            assert A.numel() == n * n and A.is_contiguous()
+            return A, C.c_void_p(A.data_ptr())
+        Af = np.asfortranarray(A, dtype=np.float64)
+        assert Af.shape == (n, n)
+        return Af, C.c_void_p(Af.ctypes.data)
+
+    def generate_matrix(self, n: int) -> np.ndarray:
+        """call generate_matrix(H, n)  (hilbert::generate_matrix, src/problems/hilbert.f90:6)."""
+        self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_HOST))
+        H = np.zeros((n, n), order="F")
+        self._chk(self._L.kl_generate_matrix(self._h, C.c_void_p(H.ctypes.data), int(n)))
+        return H
+
+    def dense_matvec(self, A, x):
+        """y = matmul(A, x)  (tests/test_hilbert.f90:44-45 builds b this way)."""
+        xa, xp, dev = self._in(x)
+        n = xa.numel() if dev else xa.size
+        Aa, Ap = self._dense_in(A, n)
+        y, yp = self._out_like(xa, dev)
+        self._chk(self._L.kl_dense_matvec(self._h, Ap, n, xp, yp))
+        return y
+
+    def _gmres_dense(self, fn, A, b, m, tol):
+        ba, bp, dev = self._in(b)
+        n = ba.numel() if dev else ba.size
+        Aa, Ap = self._dense_in(A, n)
+        x, xp = self._out_like(ba, dev)
+        fe = np.zeros(m)
+        ve = np.zeros(m + 1)
+        n_out, rs = C.c_int(0), C.c_int(0)
+        rc = self._chk(fn(self._h, Ap, n, bp, xp, int(m), float(tol), fe.ctypes.data_as(_dp),
+                          ve.ctypes.data_as(_dp), C.byref(n_out), C.byref(rs)),
+                       allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        return GmresResult(x, fe, ve, n_out.value, rs.value, rc, self.history(), self.stats())
+
+    def gmres_mgsr_dense(self, A, b, m, tol):
+        return self._gmres_dense(self._L.kl_gmres_mgsr_dense, A, b, m, tol)
+
+    def gmres_hh_dense(self, A, b, m, tol):
+        return self._gmres_dense(self._L.kl_gmres_hh_dense, A, b, m, tol)
 
     # -- CG / BiCGSTAB
     def _cg(self, fn, A, b, tol, it, M, params, nx, ny, with_pc):

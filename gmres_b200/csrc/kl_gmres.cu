@@ -450,7 +450,7 @@ int gram_lower(Ctx *c, const double *V, size_t ldv, size_t n, int k, double *d_g
     return KL_OK;
 }
 
-static int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
+int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
                             int m, double tol, double *final_err, double *v_err, int *n_out_p,
                             int *restart_out_p, const kl_precond_t *M, const double *params, int nparams,
                             int mf) {

@@ -428,14 +428,14 @@ static int hh_chain(HhRun &R, double *v, int first, int last, int dir, bool gate
     return KL_OK;
 }
 
-static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m,
+int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m,
                           double tol, double *final_err, double *v_err, int *n_out_p, int *stages_out_p,
                           const kl_precond_t *M, const double *params, int nparams, int prec_variant) {
     if (!c || !A || !b || !x || !final_err || !v_err || !n_out_p || !stages_out_p) return KL_ERR_INVALID;
     if (m < 1 || m + 1 > kMaxCols) return c->fail(KL_ERR_INVALID, "restart length m out of range");
     if (c->nranks > 1) return c->fail(KL_ERR_UNSUPPORTED, "Householder GMRES is single-GPU in this release");
     Prob P;
-    KL_TRY(prob_init(&P, c, A, prec_variant ? M : nullptr, params, nparams, nx, ny));
+    KL_TRY(prob_init(&P, c, A, prec_variant == 1 ? M : nullptr, params, nparams, nx, ny));
     const bool prec = P.pc.kind != KL_PC_NONE;
     const size_t n = P.n;
     if ((size_t)m + 1 >= n) return c->fail(KL_ERR_INVALID, "m must be smaller than the number of unknowns");
@@ -469,7 +469,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     G.hvec2 = G.hvec;
     double *d_gram = ws_take<double>(c, (size_t)(m + 2) * (m + 2));
     G.S = c->d_S; G.I = c->d_I; G.hist = c->d_hist; G.hist_cap = c->hist_cap;
-    G.m = m; G.ldh = ldh; G.mf = 0;
+    G.m = m; G.ldh = ldh; G.mf = (prec_variant == 2) ? 1 : 0;   // 2 = gmres_hh_dense: h_val < tol also stops (gmres_hh.f90:88)
     HhRun R{c, &P, G, Pm, ldv, n, 0.0};
     const bool blocked = c->opt_hh_mode == KL_HH_BLOCKED && ts_tma_ok(c, n, ldv, m);
     HhWy W;
@@ -634,6 +634,7 @@ static int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
         stages_out = k;                                                    // :381
         if (c->h_pinned_i[I_BREAKDOWN]) { status = KL_BREAKDOWN; break; }
         if (c->h_pinned[S_RES] < tol) { status = KL_OK; break; }           // :382
+        if (prec_variant == 2 && c->h_pinned[S_HVAL] < tol) { status = KL_OK; break; }   // gmres_hh.f90:108 (dense)
     }
     KL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     KL_TRY(stage_out(c, x, dx, n));

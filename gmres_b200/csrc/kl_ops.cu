@@ -9,13 +9,17 @@ namespace kl {
 int prob_init(Prob *P, Ctx *c, const kl_operator_t *op, const kl_precond_t *pc, const double *params,
               int nparams, int nx, int ny) {
     if (!c || !op) return KL_ERR_INVALID;
-    if (nx < 2 || ny < 2) return c->fail(KL_ERR_INVALID, "grid must be at least 2x2");
+    if (op->kind == KL_OP_DENSE) {
+        if (nx < 2 || ny != 1) return c->fail(KL_ERR_INVALID, "dense operator: nx = n >= 2, ny = 1");
+        if (!op->user) return c->fail(KL_ERR_INVALID, "KL_OP_DENSE without a matrix");
+        if (c->nranks > 1) return c->fail(KL_ERR_UNSUPPORTED, "dense operators are single-GPU only");
+    } else if (nx < 2 || ny < 2) return c->fail(KL_ERR_INVALID, "grid must be at least 2x2");
     P->c = c;
     P->op = *op;
     if (pc) P->pc = *pc;
     else P->pc = kl_precond_t{KL_PC_NONE, 0, nullptr, nullptr};
     if (P->op.kind != KL_OP_POISSON5 && P->op.kind != KL_OP_POISSON5_BRANCHY &&
-        P->op.kind != KL_OP_ANISO5 && P->op.kind != KL_OP_USER)
+        P->op.kind != KL_OP_ANISO5 && P->op.kind != KL_OP_USER && P->op.kind != KL_OP_DENSE)
         return c->fail(KL_ERR_INVALID, "unknown operator kind");
     if (P->op.kind == KL_OP_USER && !P->op.fn) return c->fail(KL_ERR_INVALID, "KL_OP_USER without callback");
     if (P->op.kind == KL_OP_USER && c->nranks > 1)
@@ -76,6 +80,7 @@ int halo_exchange_lines(Prob *P, const double *const *vecs, int nvec, int nlines
 
 int op_apply(Prob *P, const double *x, double *y, bool gated) {
     Ctx *c = P->c;
+    if (P->op.kind == KL_OP_DENSE) return launch_gemv(c, (const double *)P->op.user, P->nx, x, y, gated);
     if (!P->builtin_op()) {
         // user callbacks cannot be gated on the device flag; they run unconditionally
         int rc = P->op.fn(P->op.user, x, y, P->nx, P->nyl, (void *)c->stream);

@@ -14,7 +14,9 @@ struct Prob {
     int nx, ny;        // global grid
     int nyl, j0;       // this rank's slab
     size_t n;          // nx * nyl
-    bool builtin_op() const { return op.kind != KL_OP_USER; }
+    bool builtin_op() const {   // the stencil operators (fused kernels); user callbacks and dense matrices take the generic path
+        return op.kind == KL_OP_POISSON5 || op.kind == KL_OP_POISSON5_BRANCHY || op.kind == KL_OP_ANISO5;
+    }
 };
 
 int prob_init(Prob *P, Ctx *c, const kl_operator_t *op, const kl_precond_t *pc, const double *params,
@@ -55,6 +57,15 @@ inline void set_gate(F &f, const Ctx *c, bool gated, int step = 0, int run_on_co
 
 // y = A x
 int op_apply(Prob *P, const double *x, double *y, bool gated);
+// y = matmul(A, x) for a dense column-major n x n matrix in device memory (kl_dense.cu)
+int launch_gemv(Ctx *c, const double *dA, int n, const double *x, double *y, bool gated);
+// solver bodies shared by the stencil and the dense entry points
+int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m, double tol,
+                     double *final_err, double *v_err, int *n_out_p, int *restart_out_p, const kl_precond_t *M,
+                     const double *params, int nparams, int mf);
+int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny, int m, double tol,
+                   double *final_err, double *v_err, int *n_out_p, int *stages_out_p, const kl_precond_t *M,
+                   const double *params, int nparams, int prec_variant);
 // z = b - A x
 int op_resid(Prob *P, const double *x, const double *b, double *z, bool gated);
 // z = M^-1 r ; mode 0: no reduction, 1: S_RED[0] = sum z*z, 2: S_RED[0] = sum r*z.

@@ -62,6 +62,8 @@ enum {
     KL_OP_POISSON5 = 0,          /* poisson::stvec        src/problems/poisson.f90:33-77 */
     KL_OP_POISSON5_BRANCHY = 1,  /* poisson::stv_poisson  src/problems/poisson.f90:79-96 */
     KL_OP_ANISO5 = 2,            /* constant-coefficient anisotropic diffusion (README.md:46, new) */
+    KL_OP_DENSE = 3,             /* dense column-major n x n matrix in device memory (`user`), nx = n, ny = 1;
+                                    set up by kl_gmres_mgsr_dense / kl_gmres_hh_dense (single GPU only)   */
     KL_OP_USER = 100             /* user callback on device pointers (single GPU only) */
 };
 typedef struct {
@@ -183,6 +185,25 @@ int kl_gmres_hh_prec_omp(kl_handle_t h, const kl_operator_t *Ax_vec, const doubl
                          int nx, int ny, int m, double tol, double *final_err, double *v_err,
                          int *n_out, int *stages_out, const kl_precond_t *m_inv,
                          const double *params, int nparams);
+/* ---- dense-operator variants (small n: O(n^2) storage) ------------------------------------
+ * A is the Fortran array A(n,n): column-major, leading dimension n; host or device pointer
+ * according to kl_set_pointer_mode (a host matrix is copied to the device inside the call).
+ * w = matmul(A, v) is evaluated as the column sweep y(:) = y(:) + A(:,j)*v(j), j = 1..n (every
+ * y(i) a sequential FMA sum over j).  Semantics: in-cycle exit on h_val < tol or
+ * final_err(j) < tol, no preconditioner.
+ * gmres_mgsr_dense(A,b,x,m,tol,final_err,v_err,n_out,restart_out)   src/gmres_mgsr.f90:11-95  */
+int kl_gmres_mgsr_dense(kl_handle_t h, const double *A, int n, const double *b, double *x, int m, double tol,
+                        double *final_err, double *v_err, int *n_out, int *restart_out);
+/* gmres_hh_dense(A,b,x,m,tol,final_err,v_err,n_out,stages_out)       src/gmres_hh.f90:10-112
+ * (requires m + 1 < n; the reference's `if (j < n)` branch for m >= n is not provided)        */
+int kl_gmres_hh_dense(kl_handle_t h, const double *A, int n, const double *b, double *x, int m, double tol,
+                      double *final_err, double *v_err, int *n_out, int *stages_out);
+/* hilbert::generate_matrix(H, n)  src/problems/hilbert.f90:6-18: H(i,j) = 1/real(i+j-1), the quotient
+ * in SINGLE precision (default real) widened to double, as the reference computes it.          */
+int kl_generate_matrix(kl_handle_t h, double *H, int n);
+/* y = matmul(A, x) (the drivers build b = matmul(A, 1) this way, tests/test_hilbert.f90:44-45) */
+int kl_dense_matvec(kl_handle_t h, const double *A, int n, const double *x, double *y);
+
 /* cg(Ax_op,b,x,tol,iter,res) src/cg.f90:11 ; cg_omp(...) src/cg.f90:83
  * iter: maximum on entry, count on exit (unchanged if not converged).        */
 int kl_cg(kl_handle_t h, const kl_operator_t *Ax_op, const double *b, double *x, int nx, int ny,

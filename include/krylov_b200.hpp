@@ -122,6 +122,33 @@ inline int gmres_hh_prec_omp(Handle &h, const kl_operator_t &Ax_vec, const std::
     return h.check(kl_gmres_hh_prec_omp(h.get(), &Ax_vec, b.data(), x.data(), ns, ns, m, tol, final_err.data(),
                                         v_err.data(), &n_out, &stages_out, &m_inv, params.data(), (int)params.size()));
 }
+// ---- dense-operator variants: A is column-major n x n (A[i + j*n] = A(i,j)) like the Fortran array ----
+// gmres_mgsr_dense(A,b,x,m,tol,final_err,v_err,n_out,restart_out)   src/gmres_mgsr.f90:11
+inline int gmres_mgsr_dense(Handle &h, const std::vector<double> &A, const std::vector<double> &b, std::vector<double> &x,
+                            int m, double tol, std::vector<double> &final_err, std::vector<double> &v_err, int &n_out,
+                            int &restart_out) {
+    x.assign(b.size(), 0.0); final_err.assign(m, 0.0); v_err.assign(m + 1, 0.0);
+    return h.check(kl_gmres_mgsr_dense(h.get(), A.data(), (int)b.size(), b.data(), x.data(), m, tol, final_err.data(),
+                                       v_err.data(), &n_out, &restart_out));
+}
+// gmres_hh_dense(A,b,x,m,tol,final_err,v_err,n_out,stages_out)       src/gmres_hh.f90:10
+inline int gmres_hh_dense(Handle &h, const std::vector<double> &A, const std::vector<double> &b, std::vector<double> &x,
+                          int m, double tol, std::vector<double> &final_err, std::vector<double> &v_err, int &n_out,
+                          int &stages_out) {
+    x.assign(b.size(), 0.0); final_err.assign(m, 0.0); v_err.assign(m + 1, 0.0);
+    return h.check(kl_gmres_hh_dense(h.get(), A.data(), (int)b.size(), b.data(), x.data(), m, tol, final_err.data(),
+                                     v_err.data(), &n_out, &stages_out));
+}
+// generate_matrix(H, n)   src/problems/hilbert.f90:6   (callee allocates)
+inline void generate_matrix(Handle &h, std::vector<double> &H, int n) {
+    H.assign((size_t)n * n, 0.0);
+    h.check(kl_generate_matrix(h.get(), H.data(), n));
+}
+// b = matmul(A, x)
+inline void matmul(Handle &h, const std::vector<double> &A, const std::vector<double> &x, std::vector<double> &y) {
+    y.assign(x.size(), 0.0);
+    h.check(kl_dense_matvec(h.get(), A.data(), (int)x.size(), x.data(), y.data()));
+}
 // iter: maximum on entry, count on exit (unchanged if not converged) -- cg.f90:15
 inline int cg_omp(Handle &h, const kl_operator_t &Ax_op, const std::vector<double> &b, std::vector<double> &x, double tol,
                   int &iter, double &res) {

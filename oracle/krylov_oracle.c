@@ -690,6 +690,121 @@ int ko_gmres_hh(ko_stencil_fn Ax_vec, const double *b, int64_t n, double *x, int
 }
 
 /* --------------------------------------------------------------------- */
+/* dense-operator variants: gmres_mgsr_dense (src/gmres_mgsr.f90:11-95),  */
+/* gmres_hh_dense (src/gmres_hh.f90:10-112), hilbert::generate_matrix      */
+/* (src/problems/hilbert.f90:6-18)                                         */
+/* --------------------------------------------------------------------- */
+/* A is column-major n x n like the Fortran array.  matmul(A, v): libgfortran's
+ * matmul_r8 blocks and unrolls this product in a way that cannot be restated
+ * without the library; the oracle (and the CUDA kernel) define it as the
+ * column sweep  y = 0 ; do j: y(:) = y(:) + A(:,j)*v(j)  with FMA, i.e. every
+ * y(i) is a sequential sum over j.  PARITY UNPINNED beyond that. */
+static const double *g_dense_A = NULL;
+static int64_t g_dense_n = 0;
+void ko_set_dense(const double *A, int64_t n) { g_dense_A = A; g_dense_n = n; }
+void ko_dense_matvec(const double *x, double *y, int nsize_unused)
+{
+    (void)nsize_unused;
+    const int64_t n = g_dense_n;
+    const double *A = g_dense_A;
+    for (int64_t i = 0; i < n; ++i) y[i] = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        const double xj = x[j];
+        const double *col = A + j * n;
+        for (int64_t i = 0; i < n; ++i) y[i] = fma(col[i], xj, y[i]);
+    }
+}
+ko_stencil_fn ko_get_dense(void) { return ko_dense_matvec; }
+
+/* hilbert.f90:13-17  H(i,j) = 1 / real(i+j-1): real() is default (single)
+ * precision, so the quotient is a float that is then widened to double. */
+void ko_generate_matrix(double *H, int n)
+{
+    for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) H[(int64_t)(i - 1) + (int64_t)(j - 1) * n] = (double)(1.0f / (float)(i + j - 1));
+}
+
+/* gmres_hh.f90:10-112 gmres_hh_dense: serial Householder GMRES on the dense
+ * operator set by ko_set_dense; in-cycle exit on h_val < tol or final_err < tol. */
+int ko_gmres_hh_dense(const double *b, int64_t n, double *x, int m, double tol, double *final_err,
+                      double *v_err, int *n_out_p, int *stages_out_p, int max_stages,
+                      double *history, int history_cap, int *history_len)
+{
+    if (max_stages <= 0) max_stages = KO_HH_STAGES;
+    double *P = malloc(sizeof(double) * (size_t)n * (m + 1));
+    double *H = calloc((size_t)(m + 1) * m, sizeof(double));
+    double *y = calloc(m, sizeof(double)), *v_j = calloc(n, sizeof(double));
+    double *w = calloc(n, sizeof(double)), *g = calloc(m + 1, sizeof(double));
+    double *cs = calloc(m, sizeof(double)), *sn = calloc(m, sizeof(double));
+    if (!P || !H || !y || !v_j || !w || !g || !cs || !sn) return -1;
+    const int ldh = m + 1;
+    int n_out = 0, stages_out = max_stages, hl = 0;
+    double h_val = 0.0;
+    memset(x, 0, sizeof(double) * n);
+    memset(final_err, 0, sizeof(double) * m);
+    memset(v_err, 0, sizeof(double) * (m + 1));
+    double beta0 = ko_norm2(b, n);                                      /* :34 */
+    for (int k = 1; k <= max_stages; ++k) {
+        memset(g, 0, sizeof(double) * (m + 1));                         /* :36 */
+        memset(H, 0, sizeof(double) * (size_t)(m + 1) * m);
+        memset(P, 0, sizeof(double) * (size_t)n * (m + 1));
+        ko_dense_matvec(x, w, 0);                                       /* :37 */
+        for (int64_t t = 0; t < n; ++t) w[t] = b[t] - w[t];
+        double beta = ko_norm2(w, n);                                   /* :38 */
+        g[0] = -copysign(beta, w[0]);                                   /* :39 */
+        w[0] = copysign(beta, w[0]) + w[0];                             /* :40 */
+        double nw = ko_norm2(w, n);
+        for (int64_t t = 0; t < n; ++t) P[t] = w[t] / nw;               /* :41 */
+        int stop = 0;
+        for (int j = 0; j < m; ++j) {
+            n_out = j + 1;
+            for (int64_t t = 0; t < n; ++t) v_j[t] = 0.0;               /* :44 */
+            v_j[j] = 1.0;
+            for (int i = j; i >= 0; --i) {                              /* :45-47 */
+                const double *p = P + (int64_t)i * n;
+                double d = ko_dot(v_j, p, n);
+                for (int64_t t = 0; t < n; ++t) v_j[t] = fma(-(2.0 * p[t]), d, v_j[t]);
+            }
+            ko_dense_matvec(v_j, w, 0);                                 /* :48 */
+            for (int i = 0; i <= j; ++i) {                              /* :49-51 */
+                const double *p = P + (int64_t)i * n;
+                double d = ko_dot(w, p, n);
+                for (int64_t t = 0; t < n; ++t) w[t] = fma(-(2.0 * p[t]), d, w[t]);
+            }
+            ko_hh_single_block(H, ldh, P, n, w, cs, sn, g, j, &h_val);  /* :52-85 */
+            final_err[j] = fabs(g[j + 1]) / beta0;                      /* :87 */
+            if (history && hl < history_cap) history[hl] = final_err[j];
+            ++hl;
+            if (h_val < tol || final_err[j] < tol) {                    /* :88-92 */
+                n_out = j + 1;
+                stages_out = k;
+                stop = 1;
+                break;
+            }
+        }
+        ko_backsolve(H, ldh, g, y, m, n_out);                           /* :95-99 */
+        for (int64_t t = 0; t < n; ++t) w[t] = 0.0;                     /* :101-102 */
+        for (int i = 0; i < n_out; ++i) w[i] = y[i];
+        for (int i = n_out - 1; i >= 0; --i) {                          /* :103-105 */
+            const double *p = P + (int64_t)i * n;
+            double d = ko_dot(p, w, n);
+            for (int64_t t = 0; t < n; ++t) w[t] = fma(-(2.0 * p[t]), d, w[t]);
+        }
+        for (int64_t t = 0; t < n; ++t) x[t] = x[t] + w[t];             /* :106 */
+        if (stop || h_val < tol || final_err[n_out - 1] < tol) {        /* :108-111 */
+            stages_out = k;
+            break;
+        }
+    }
+    ko_calculate_verr(P, n, w, y, v_err, n_out);                        /* :113 */
+    *n_out_p = n_out;
+    *stages_out_p = stages_out;
+    if (history_len) *history_len = hl;
+    free(P); free(H); free(y); free(v_j); free(w); free(g); free(cs); free(sn);
+    return 0;
+}
+
+/* --------------------------------------------------------------------- */
 /* src/cg.f90                                                            */
 /* --------------------------------------------------------------------- */
 

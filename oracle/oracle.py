@@ -122,8 +122,8 @@ class GmresResult:
     orth_frob: float = float("nan")
 
     @property
-    def iterations(self) -> int:  # tests/test_poisson_mf.f90:78
-        return 0  # set by caller (needs m)
+    def iterations(self) -> int:  # tests/test_poisson_mf.f90:78  (restart_out - 1) * m + n_out, m = size(final_err)
+        return (self.restart_out - 1) * int(self.final_err.size) + self.n_out
 
 
 @dataclass
@@ -188,6 +188,55 @@ def gmres_hh(Ax_vec, b, m, tol, M_inv=None, params=(0.0, 0.0), max_stages=0, ski
     assert rc == 0
     return GmresResult(x, fe, ve, n_out.value, st.value, h[: min(hl.value, history_cap)].copy(),
                        orth.value)
+
+
+# ---- dense-operator variants (gmres_mgsr.f90:11, gmres_hh.f90:10, hilbert.f90:6) ----
+_dense_keep = None
+
+
+def dense_fn(A: np.ndarray):
+    """A(n,n) as the Fortran array (column-major storage): pass a numpy array whose [i, j] is A(i,j)."""
+    global _dense_keep
+    Af = np.asfortranarray(A, dtype=np.float64)
+    _dense_keep = Af
+    lib().ko_set_dense(Af.ctypes.data_as(_dp), C.c_int64(Af.shape[0]))
+    lib().ko_get_dense.restype = STENCIL_FN
+    return lib().ko_get_dense()
+
+
+def generate_matrix(n: int) -> np.ndarray:
+    """hilbert::generate_matrix (single-precision reciprocals widened to double)."""
+    H = np.zeros((n, n), order="F")
+    lib().ko_generate_matrix(H.ctypes.data_as(_dp), int(n))
+    return H
+
+
+def dense_matvec(A: np.ndarray, x: np.ndarray) -> np.ndarray:
+    f = dense_fn(A)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    f(_p(x), _p(y), 0)
+    return y
+
+
+def gmres_mgsr_dense(A, b, m, tol, max_restarts=0, history_cap=200000):
+    """gmres_mgsr.f90:11-95 = the _mf algorithm on w = matmul(A, v) without preconditioner."""
+    lib().ko_get_identity.restype = PRECOND_FN
+    return gmres_mgsr_mf(dense_fn(A), b, m, tol, lib().ko_get_identity(), (0.0, 0.0), max_restarts, 0, history_cap)
+
+
+def gmres_hh_dense(A, b, m, tol, max_stages=0, history_cap=200000):
+    f = dense_fn(A)  # noqa: F841  (sets the global operator)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = b.size
+    x = np.zeros(n); fe = np.zeros(m); ve = np.zeros(m + 1)
+    n_out = C.c_int(0); st = C.c_int(0)
+    h, hl = _hist(history_cap)
+    rc = lib().ko_gmres_hh_dense(_p(b), C.c_int64(n), _p(x), int(m), C.c_double(tol), _p(fe), _p(ve),
+                                 C.byref(n_out), C.byref(st), int(max_stages), _p(h), int(history_cap),
+                                 C.byref(hl))
+    assert rc == 0
+    return GmresResult(x, fe, ve, n_out.value, st.value, h[: min(hl.value, history_cap)].copy())
 
 
 def _cg_like(fn, A, b, tol, max_iter, M_inv, params, history_cap):

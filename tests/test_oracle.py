@@ -205,3 +205,44 @@ def test_extras_aniso_cheb_lanczos(ko):
     r1 = ko.pcg_omp(A, b, 1e-9, 10000, ko.cbpr2_fn(), P)
     r4 = ko.pcg_omp(A, b, 1e-9, 10000, ko.cheb_fn(4), (0.2, 8.2))
     assert r4.iter < r1.iter and np.abs(r4.x - 1).max() < 1e-8
+
+
+# ---- dense-operator variants (gmres_mgsr.f90:11-95, gmres_hh.f90:10-112, hilbert.f90:6-18) ----
+def _dense_poisson(ns):
+    """the 5-point operator as an explicit matrix (what tests/test_poisson.f90 feeds the dense solvers)"""
+    n = ns * ns
+    A = np.zeros((n, n))
+    for j in range(ns):
+        for i in range(ns):
+            k = i + j * ns
+            A[k, k] = 4.0
+            if i > 0: A[k, k - 1] = -1.0
+            if i < ns - 1: A[k, k + 1] = -1.0
+            if j > 0: A[k, k - ns] = -1.0
+            if j < ns - 1: A[k, k + ns] = -1.0
+    return A
+
+
+def test_dense_oracle_matches_matrix_free(ko):
+    ns = 12
+    A = _dense_poisson(ns)
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    assert np.array_equal(ko.dense_matvec(A, np.ones(ns * ns)), b)
+    d = ko.gmres_mgsr_dense(A, b, 30, 1e-10)
+    f = ko.gmres_mgsr_mf(ko.stvec_fn(), b, 30, 1e-10, ko.identity_fn(), (0.0, 0.0))
+    assert (d.restart_out, d.n_out) == (f.restart_out, f.n_out)
+    assert np.allclose(d.x, f.x, rtol=0, atol=1e-12) and np.abs(d.x - 1).max() < 1e-8
+    hd = ko.gmres_hh_dense(A, b, 30, 1e-10)
+    assert abs(hd.iterations - d.iterations) <= 1 and np.abs(hd.x - 1).max() < 1e-8
+    assert hd.v_err[: hd.n_out].max() < 1e-26        # README.md:10 Householder orthogonality claim
+
+
+def test_hilbert_matrix_and_dense_solvers(ko):
+    H = ko.generate_matrix(12)
+    i, j = np.meshgrid(np.arange(1, 13), np.arange(1, 13), indexing="ij")
+    assert np.array_equal(H, (np.float32(1) / (i + j - 1).astype(np.float32)).astype(np.float64))
+    b = ko.dense_matvec(H, np.ones(12))
+    for r in (ko.gmres_mgsr_dense(H, b, 10, 1e-15), ko.gmres_hh_dense(H, b, 10, 1e-15)):
+        # tests/test_hilbert.f90: tol 1e-15 on a cond ~1e16 matrix: the residual estimate reaches the
+        # tolerance while x is only accurate to cond * eps
+        assert r.final_err[r.n_out - 1] < 1e-15 and np.abs(r.x - 1).max() < 1e-3
