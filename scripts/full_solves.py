@@ -40,4 +40,33 @@ if "gmres4096" in which:
         l2_err=float(torch.linalg.vector_norm(r.x - 1)), lanczos_ritz=(lo, hi), lanczos_params=prm,
         roofline_frac=r.stats["algorithmic_bytes"] / (r.stats["solve_ms"] * 1e-3) / 1e9 / 6547.2)
     print(json.dumps(out), flush=True)
+for key in which:
+    # degree-k Chebyshev preconditioner, k operator applications in one HBM pass (kl_chain_tma.cuh), interval
+    # [b/ratio, b] with b = 1.025 * largest Lanczos(30) Ritz value:  gmres4096chebK / pcg16384chebK
+    if "cheb" not in key:
+        continue
+    solver, k = key.split("cheb")[0], int(key.split("cheb")[1])
+    n = 4096 if solver.startswith("gmres") else 16384
+    m = 95
+    b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
+    t0 = time.perf_counter()
+    lo, hi = h.lanczos(kl.stvec, n, n, 30)
+    prm = (1.025 * hi, 1.025 * hi / 1000.0)
+    if solver.startswith("gmres"):
+        r = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cheb(k), prm, nx=n, ny=n)
+        its = (r.restart_out - 1) * m + r.n_out
+        extra = dict(cycles=r.restart_out, n_out=r.n_out, final_err=float(r.final_err[r.n_out - 1]))
+    else:
+        h.set_option(4, 64)
+        r = h.pcg_omp(kl.stvec, b, 1e-9, 200000, kl.cheb(k), prm, nx=n, ny=n)
+        its = r.iter
+        extra = dict(res=r.res)
+    dt = time.perf_counter() - t0
+    out[f"{solver}+cheb({k}) {n}^2 (Lanczos bounds, incl. the Lanczos run)"] = dict(
+        status=r.status, iterations=its, seconds=dt, solve_seconds=r.stats["solve_ms"] * 1e-3,
+        its_per_s=its / (r.stats["solve_ms"] * 1e-3), linf_err=float((r.x - 1).abs().max()),
+        lanczos_ritz=(lo, hi), params=prm, **extra)
+    print(json.dumps(out), flush=True)
+    del b, r
+    torch.cuda.empty_cache()
 json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "full_solves.json"), "w"), indent=1)
