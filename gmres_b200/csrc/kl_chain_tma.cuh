@@ -88,6 +88,9 @@ struct ChainBase {
     static constexpr int NC = NC_;
     static constexpr int NRED = NRED_;
     static constexpr int NSIDE = 0;     // point-wise side inputs of the last level, prefetched 2 lines ahead
+    // Two columns per thread.  A four-column variant (half the shuffles and per-line overhead per point, but
+    // ~160 registers at L = 2, i.e. 3 CTAs per SM instead of 6) measured 10-50 % slower: these kernels are
+    // dependent FP64 chains behind a shuffle and live on thread-level parallelism.
     // ring: 1 input: 3-line stages, 18 / 24 lines ; more inputs: 1-line stages, 6 lines (a CTA needs ~2 us per
     // line, so three lines of lookahead cover the DRAM latency; small rings buy 6 CTAs per SM instead)
     static constexpr int SR = NIN_ == 1 ? 3 : 1;
