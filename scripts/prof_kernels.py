@@ -15,6 +15,12 @@ if which in ("all", "pcg"):
     h.set_option(4, 8)
     r = h.pcg_omp(kl.stvec, b, 0.0, 4, kl.cbpr2, (8.2, 0.2), nx=n, ny=n)
     print("pcg", r.stats["solve_ms"])
+if which in ("all", "cg"):
+    n = 8192
+    b = rhs(kl.stvec, n, n)
+    h.set_option(4, 8)
+    r = h.cg_omp(kl.stvec, b, 0.0, 3, nx=n, ny=n)
+    print("cg", r.stats["solve_ms"])
 if which in ("all", "gmres"):
     n = 4096
     b = rhs(kl.stvec, n, n)
