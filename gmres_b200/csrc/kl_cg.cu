@@ -4,7 +4,8 @@
 // All four share one device implementation (the serial and OpenMP variants
 // compute the same quantities; only their summation order differs).
 //
-// Per iteration (fused path, built-in operator), 72n B for CG and 80n B for PCG + cbpr2:
+// Plain CG (default): 64n B per iteration, see FCgDirX2 / FCgRUpdate below (A applied twice, A p never stored).
+// KL_OPT_CHAIN = 0 and PCG + cbpr2 -- per iteration 72n B for CG and 80n B for PCG + cbpr2:
 //   K1  x += alpha_prev*p ; p' = z + beta*p ; ax = A p' ; ax.p'   reads z,p,x  writes p',ax,x   48n B
 //   K2  r -= alpha ax ; r.r                                       reads r,ax   writes r         24n B
 //       (pcg + cbpr2: r' = r - alpha ax ; z = cbpr2(r') ; r'.r' ; r'.z in one stencil pass     32n B)
@@ -88,6 +89,58 @@ struct FCgDirX : StencilBase<2, 1> {
     }
 };
 
+// ---- plain CG with the operator applied twice instead of storing A p (64n B per iteration) ---------------
+// K1: x += alpha_prev * p_old ; p_new = r + beta*p_old ; acc0 = (A p_new).p_new      reads r,p,x  writes p',x  40n
+// K2: p_new = r + beta*p_old again (same fma => same bits) ; ax = A p_new ; r' = r - alpha ax ; acc0 = r'.r'
+//                                                                                  reads r,p    writes r'    24n
+// A p is never written to or read from HBM: five FP64 operations per point are cheaper than 16 bytes.  K2
+// reuses the halo lines K1 exchanged (r and p_old have not changed), so there is no second exchange.
+struct FCgDirX2 : StencilBase<2, 1> {
+    double *p_new, *x_new;     // x is ping-ponged like p and r: out-of-place streams reach a higher HBM efficiency
+    const double *x;
+    const double *S;
+    double beta, alpha_prev;
+    __device__ __forceinline__ void init() {
+        beta = S[S_BETA];
+        alpha_prev = S[S_ALPHA];
+    }
+    __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
+    template <int VEC>
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        double vx[VEC];
+        KL_LD(VEC, vx, x, idx)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            vx[v] = fma(alpha_prev, raw[1][v], vx[v]);        // cg.f90:128 of the previous iteration
+            acc[0] = fma(au[v], cu[v], acc[0]);               // :118-122
+        }
+        KL_ST(VEC, x_new, idx, vx)
+        KL_ST(VEC, p_new, idx, cu)
+    }
+};
+struct FCgRUpdate : StencilBase<2, 1> {
+    double *r_new;
+    const double *S;
+    double beta, alpha;
+    __device__ __forceinline__ void init() {
+        beta = S[S_BETA];      // still the beta K1 used: PostCgEnd replaces it only after this kernel's last block
+        alpha = S[S_ALPHA];
+    }
+    __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
+    template <int VEC>
+    __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
+                                          const double (&au)[VEC], double *acc) const {
+        double rn[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            rn[v] = fma(-alpha, au[v], raw[0][v]);            // cg.f90:130
+            acc[0] = fma(rn[v], rn[v], acc[0]);               // :131-133
+        }
+        KL_ST(VEC, r_new, idx, rn)
+    }
+};
+
 // K2 without x: r -= alpha ax ; acc0 = sum r*r     (cg.f90:130-133)
 struct PCgUpdateR : PwBase<1> {
     double *r;
@@ -161,14 +214,16 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
     const bool fuse_pc = fused && P.pc.kind == KL_PC_CBPR2;   // update + cbpr2 in one pass
     const bool defer_x = fused && (!prec || fuse_pc);         // x update folded into the next K1 (72n / 80n B)
-    const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0) + (fuse_pc ? 1 : 0);
+    const bool twice = defer_x && !prec && c->opt_chain;       // plain CG: apply A twice, never store A p (64n B)
+    const int nvec = 4 + (dev ? 0 : 1) + (prec ? 3 : 0) + ((fuse_pc || twice) ? 1 : 0) + (twice ? 1 : 0);
     KL_TRY(ws_reserve(c, nvec * ws_need(n)));
     ws_reset(c);
     double *r = ws_take<double>(c, n), *p0 = ws_take<double>(c, n), *p1 = ws_take<double>(c, n);
     double *ax = ws_take<double>(c, n);
     double *dx = dev ? x : ws_take<double>(c, n);
     double *z = r, *aux = nullptr, *aux2 = nullptr;
-    double *r_alt = fuse_pc ? ws_take<double>(c, n) : nullptr;
+    double *r_alt = (fuse_pc || twice) ? ws_take<double>(c, n) : nullptr;
+    double *x_cur = dx, *x_alt = twice ? ws_take<double>(c, n) : nullptr;
     const Cbpr2Coef cf = fuse_pc ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
     if (prec) {
         z = ws_take<double>(c, n);
@@ -207,6 +262,32 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
         if (batch > maxit - done) batch = maxit - done;
         for (int k = 0; k < batch; ++k) {
             // ---- K1
+            if (twice) {
+                Halo H;
+                const double *vecs[2] = {r, pold};
+                KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                {
+                    ProfScope ps(c, 0, "cg_xdir_dot (stencil: x+=alpha_prev*p; p=r+beta*p; (A p).p)", 40.0 * n);
+                    FCgDirX2 f;
+                    set_io(f, &P, vecs, H);
+                    set_gate(f, c, true);
+                    f.p_new = pnew; f.x = x_cur; f.x_new = x_alt; f.S = c->d_S;
+                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgAlpha{c->d_S}));
+                    std::swap(x_cur, x_alt);
+                }
+                {
+                    ProfScope ps(c, 1, "cg_apply_rupdate_dot (stencil: r-=alpha*A(r+beta*p); r.r)", 24.0 * n);
+                    FCgRUpdate f;
+                    set_io(f, &P, vecs, H);      // same halo lines: r and p_old are unchanged since K1
+                    set_gate(f, c, true);
+                    f.r_new = r_alt; f.S = c->d_S;
+                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}));
+                }
+                std::swap(r, r_alt);
+                z = r;
+                double *t = pold; pold = pnew; pnew = t;
+                continue;
+            }
             if (defer_x) {
                 ProfScope ps(c, 0, "cg_xdir_apply_dot (stencil: x+=alpha_prev*p; p=z+beta*p; ax=A p; ax.p)", 48.0 * n);
                 Halo H;
@@ -293,9 +374,12 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
         if (status == KL_NOT_CONVERGED) KL_TRY(read_back(c));
         const int its_done = c->h_pinned_i[I_ITER];
         if (its_done > 0) {
+            // `twice`: x is ping-ponged; K1 of iteration i read buffer (i-1)&1 and wrote buffer i&1 (0 = dx), and
+            // the K1 launches after the convergence step did nothing: the current x is in buffer its_done&1.
+            const double *xsrc = (twice && (its_done & 1)) ? ((x_cur == dx) ? x_alt : x_cur) : dx;
             PAxpy u;
             set_gate(u, c, false);
-            u.a = dx; u.b = (its_done & 1) ? p1 : p0; u.y = dx; u.S = c->d_S; u.s_idx = S_ALPHA; u.sign = 1.0;
+            u.a = xsrc; u.b = (its_done & 1) ? p1 : p0; u.y = dx; u.S = c->d_S; u.s_idx = S_ALPHA; u.sign = 1.0;
             KL_TRY(launch_pointwise(c, u, n, NoPost{}));
         }
     }
@@ -316,7 +400,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     c->stats.cycles = polls;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
-    c->stats.algorithmic_bytes = (double)its * (fuse_pc ? 80.0 : (prec ? 96.0 : (defer_x ? 72.0 : 80.0))) * (double)n;
+    c->stats.algorithmic_bytes = (double)its * (fuse_pc ? 80.0 : (prec ? 96.0 : (twice ? 64.0 : (defer_x ? 72.0 : 80.0)))) * (double)n;
     *res_out = c->h_pinned[S_RES];
     if (status == KL_OK) *iter = c->h_pinned_i[I_CONV_AT];   // count on exit; unchanged if not converged
     return status;

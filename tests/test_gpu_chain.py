@@ -112,3 +112,20 @@ def test_pbicgstab_chain_anisotropic_rectangular(kl, h):
     s = _no_chain(kl, h, lambda: h.pbicgstab_omp(A, b, 0.0, 4, kl.cbpr2, prm, nx, ny))
     assert np.allclose(g.history[:4], s.history[:4], rtol=1e-9)
     assert np.allclose(g.x, s.x, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("nx,ny", [(300, 300), (1000, 64), (128, 515)])
+def test_cg_operator_twice_matches_stored_ap(kl, h, nx, ny):
+    # default plain CG never stores A p (64n B/iteration: K2 recomputes p = r + beta*p_old and A p);
+    # KL_OPT_CHAIN = 0 keeps the variant that stores it (72n B).  Same arithmetic per point.
+    b = h.apply(kl.stvec, np.ones(nx * ny), nx, ny)
+    for its in (1, 2, 7):
+        g = h.cg_omp(kl.stvec, b, 0.0, its, nx=nx, ny=ny)
+        s = _no_chain(kl, h, lambda: h.cg_omp(kl.stvec, b, 0.0, its, nx=nx, ny=ny))
+        assert np.allclose(g.x, s.x, rtol=1e-12, atol=1e-14), (its, np.abs(g.x - s.x).max())
+        assert np.allclose(g.history, s.history, rtol=1e-12)
+    g = h.cg_omp(kl.stvec, b, 1e-9, 20000, nx=nx, ny=ny)
+    s = _no_chain(kl, h, lambda: h.cg_omp(kl.stvec, b, 1e-9, 20000, nx=nx, ny=ny))
+    assert g.status == 0 and abs(g.iter - s.iter) <= 1
+    assert g.stats["algorithmic_bytes"] / g.iter / (nx * ny) == pytest.approx(64.0)
+    assert np.abs(g.x - 1).max() < 1e-7 and np.abs(g.x - s.x).max() < 1e-9
