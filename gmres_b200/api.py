@@ -33,7 +33,7 @@ KL_PC_NONE, KL_PC_CBPR2, KL_PC_CHEB, KL_PC_USER = 0, 1, 2, 100
 KL_POINTER_HOST, KL_POINTER_DEVICE = 0, 1
 (KL_OPT_ORTHO, KL_OPT_MAX_RESTARTS, KL_OPT_VERR, KL_OPT_CHECK_EVERY, KL_OPT_USE_GRAPH,
  KL_OPT_HH_MODE, KL_OPT_FUSE, KL_OPT_PROFILE) = range(1, 9)
-KL_OPT_TMA, KL_OPT_PEER, KL_OPT_REORTH_ETA, KL_OPT_CHAIN, KL_OPT_STENCIL_ROWS = 9, 10, 11, 12, 13
+KL_OPT_TMA, KL_OPT_PEER, KL_OPT_REORTH_ETA, KL_OPT_CHAIN, KL_OPT_STENCIL_ROWS, KL_OPT_INLINE_ALLREDUCE = 9, 10, 11, 12, 13, 14
 ORTHO_MGS2, ORTHO_CGS2, ORTHO_CGS2_SELECTIVE = 0, 1, 2
 HH_SEQUENTIAL, HH_BLOCKED = 0, 1
 KL_UNIQUE_ID_BYTES = 128

@@ -235,27 +235,9 @@ static int nccl_load(std::string *err) {
 // collective ahead of a peer (it needs the peer's contribution to go further).
 // If IPC mapping is not possible the NCCL path below is used instead.
 // ------------------------------------------------------------------------
-constexpr int kArMax = 128;                 // doubles per all-reduce
-constexpr int kHaloNxCap = 65536;           // widest grid line supported by the peer path
-constexpr size_t kCbArInbox = 0;                                        // [2][16][kArMax] doubles
-constexpr size_t kCbArFlags = kCbArInbox + 2 * 16 * kArMax;             // [2][16] u64
-constexpr size_t kCbHaloFlags = kCbArFlags + 2 * 16;                    // [2][4 slots][2 dirs] u64
-constexpr size_t kCbHalo = kCbHaloFlags + 2 * 4 * 2;                    // [2][4][2][kHaloNxCap] doubles
-constexpr size_t kCbDoubles = kCbHalo + (size_t)2 * 4 * 2 * kHaloNxCap;
-constexpr long long kSpinLimit = 1ll << 27;   // ~seconds: a lost peer flags a breakdown instead of hanging
-
 struct PeerPtrs {
     double *p[16];
 };
-__device__ __forceinline__ void st_release_sys(unsigned long long *addr, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *addr) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
-    return v;
-}
-
 __global__ void k_peer_allreduce(double *buf, const int count, const PeerPtrs pp, const int rank, const int P,
                                  const unsigned long long seq, int *I) {
     const int par = (int)(seq & 1ull);
@@ -418,6 +400,15 @@ static int peer_setup(Ctx *c) {
     cudaMemcpy(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_flag);
     c->peer_ok = (flag == 0.0);
+    if (c->peer_ok) {
+        PeerCtl pc;
+        for (int r = 0; r < 16; ++r) pc.p[r] = c->cb_peer[r];
+        pc.rank = c->rank;
+        pc.nranks = c->nranks;
+        if (cudaMalloc(&c->d_peerctl, sizeof(PeerCtl)) == cudaSuccess)
+            cudaMemcpy(c->d_peerctl, &pc, sizeof(PeerCtl), cudaMemcpyHostToDevice);
+        else { cudaGetLastError(); c->d_peerctl = nullptr; }
+    }
     return KL_OK;
 }
 
@@ -474,6 +465,7 @@ int kl_destroy(kl_handle_t h) {
     for (int r = 0; r < 16; ++r)
         if (c->cb_peer[r] && c->cb_peer[r] != c->cb_local) cudaIpcCloseMemHandle(c->cb_peer[r]);
     cudaFree(c->cb_local);
+    cudaFree(c->d_peerctl);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)c->nccl_comm);
     cudaFree(c->d_S);
     cudaFree(c->d_I);
@@ -547,6 +539,7 @@ int kl_set_option(kl_handle_t h, int key, int value) {
         case KL_OPT_PROFILE: h->opt_profile = value != 0; break;
         case KL_OPT_TMA: h->opt_tma = value != 0; break;
         case KL_OPT_CHAIN: h->opt_chain = value != 0; break;
+        case KL_OPT_INLINE_ALLREDUCE: h->opt_inline_ar = value != 0; break;
         case KL_OPT_STENCIL_ROWS: h->opt_stencil_rows = value > 0 ? value : 0; break;
         case KL_OPT_REORTH_ETA:
             if (value < 1 || value > 1000) return KL_ERR_INVALID;
@@ -575,6 +568,7 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_PROFILE: *value = h->opt_profile; break;
         case KL_OPT_TMA: *value = h->opt_tma; break;
         case KL_OPT_CHAIN: *value = h->opt_chain; break;
+        case KL_OPT_INLINE_ALLREDUCE: *value = h->opt_inline_ar; break;
         case KL_OPT_STENCIL_ROWS: *value = h->opt_stencil_rows; break;
         case KL_OPT_REORTH_ETA: *value = h->opt_reorth_eta_permille; break;
         case KL_OPT_PEER: *value = h->peer_ok ? 1 : 0; break;

@@ -55,10 +55,29 @@ enum IIdx {
     I_COUNT = 64
 };
 
+// NVLink peer-memory communication buffer (one per rank, mapped into every process through CUDA IPC); layout in
+// doubles.  Used by the stand-alone collectives in kl_core.cu and by the all-reduce that the LAST BLOCK of a
+// reducing kernel performs inline (peer_allreduce_block below).
+constexpr int kArMax = 128;                 // doubles per all-reduce
+constexpr int kHaloNxCap = 65536;           // widest halo message (doubles) supported by the peer path
+constexpr size_t kCbArInbox = 0;                                        // [2][16][kArMax] doubles
+constexpr size_t kCbArFlags = kCbArInbox + 2 * 16 * kArMax;             // [2][16] u64
+constexpr size_t kCbHaloFlags = kCbArFlags + 2 * 16;                    // [2][4 slots][2 dirs] u64
+constexpr size_t kCbHalo = kCbHaloFlags + 2 * 4 * 2;                    // [2][4][2][kHaloNxCap] doubles
+constexpr size_t kCbDoubles = kCbHalo + (size_t)2 * 4 * 2 * kHaloNxCap;
+constexpr long long kSpinLimit = 1ll << 27;   // ~seconds: a lost peer flags a breakdown instead of hanging
+struct PeerCtl {             // lives in device memory (RedCtl carries a pointer to it)
+    double *p[16];           // every rank's communication buffer
+    int rank, nranks;
+};
+
 struct RedCtl {
     double *partials;        // [grid * ld]
     unsigned int *counter;   // zero between kernels
     double *red;             // local sums destination
+    const PeerCtl *peer;     // != nullptr: the last block all-reduces `red` over NVLink before the post functor
+    unsigned long long seq;  // sequence number of that all-reduce
+    int *I;                  // int block (breakdown flag for a lost peer)
 };
 
 // ------------------------------------------------------------------------
@@ -104,6 +123,8 @@ struct kl_context_s {
     double *cb_local = nullptr;          // this rank's communication buffer
     double *cb_peer[16] = {};            // every rank's buffer mapped into this process (cb_peer[rank] = cb_local)
     unsigned long long ar_seq = 0, halo_seq = 0;
+    struct kl::PeerCtl *d_peerctl = nullptr;   // device copy of the peer pointers (inline all-reduce)
+    int opt_inline_ar = 1;                     // all-reduce inside the reducing kernel's last block
     // device blocks
     double *d_S = nullptr;
     int *d_I = nullptr;
@@ -290,6 +311,49 @@ __device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc,
     }
     __syncthreads();
     return true;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *addr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *addr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+
+// One-shot all-reduce of rc.red[0..K) over NVLink peer memory, executed by ALL threads of the last block of a
+// reducing kernel (compute + collective in one kernel: no all-reduce launch, no post-functor launch).  Every
+// rank pushes its sums into every rank's inbox with posted stores, raises a release flag carrying the sequence
+// number, waits for the P flags and adds the inbox in rank order -- identical bits on every rank.  Same
+// protocol, buffers and sequence counter as k_peer_allreduce (kl_core.cu), so both can be mixed in a stream.
+template <int K>
+__device__ __forceinline__ void peer_allreduce_block(const RedCtl &rc) {
+    const PeerCtl &pc = *rc.peer;
+    const int P = pc.nranks, rank = pc.rank, par = (int)(rc.seq & 1ull);
+    for (int t = threadIdx.x; t < K * P; t += blockDim.x) {
+        const int q = t / K, i = t - q * K;
+        pc.p[q][kCbArInbox + ((size_t)par * 16 + rank) * kArMax + i] = rc.red[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < P) {
+        __threadfence_system();
+        unsigned long long *fl = reinterpret_cast<unsigned long long *>(pc.p[threadIdx.x] + kCbArFlags);
+        st_release_sys(fl + par * 16 + rank, rc.seq);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pc.p[rank] + kCbArFlags);
+        long long spins = 0;
+        while (ld_acquire_sys(mine + par * 16 + threadIdx.x) < rc.seq) {
+            if (++spins > kSpinLimit) { rc.I[I_BREAKDOWN] = 1; break; }
+        }
+    }
+    __syncthreads();
+    const double *inbox = pc.p[rank] + kCbArInbox + (size_t)par * 16 * kArMax;
+    if ((int)threadIdx.x < K) {
+        double sum = 0.0;
+        for (int r = 0; r < P; ++r) sum += __ldcg(inbox + (size_t)r * kArMax + threadIdx.x);
+        rc.red[threadIdx.x] = sum;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------
@@ -488,6 +552,7 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
         block_sum<NR, kStencilThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         if (grid_sum<NR>(acc, rc, nb, bid, &s_flag)) {
+            if (rc.peer) peer_allreduce_block<NR>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
         }
     }
@@ -519,6 +584,7 @@ k_pointwise(const F f_in, const size_t n, const RedCtl rc, const Post post, cons
         __shared__ int s_flag;
         block_sum<(NRED > 0 ? NRED : 1), kPwThreads>(acc, sm);
         if (grid_sum<(NRED > 0 ? NRED : 1)>(acc, rc, gridDim.x, blockIdx.x, &s_flag)) {
+            if (rc.peer) peer_allreduce_block<(NRED > 0 ? NRED : 1)>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
         }
     }
@@ -556,7 +622,15 @@ __global__ void k_post(const Post post, const int *flags, const int step, const 
 // ------------------------------------------------------------------------
 // launch helpers (host)
 // ------------------------------------------------------------------------
-inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED}; }
+inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED, nullptr, 0ull, c->d_I}; }
+// Reducing kernel on several GPUs with NVLink peer memory: the kernel's last block does the all-reduce and runs
+// the post functor itself.  Returns true when that path is taken (then finish_reduction must not be called).
+inline bool redctl_inline_allreduce(Ctx *c, RedCtl &rc, int nred) {
+    if (c->nranks == 1 || !c->peer_ok || !c->d_peerctl || !c->opt_inline_ar || nred > kArMax) return false;
+    rc.peer = c->d_peerctl;
+    rc.seq = ++c->ar_seq;
+    return true;
+}
 
 inline int stencil_rows(int nx, int ny, int vec) {
     // aim for >= ~8 blocks per SM, between 8 and 64 lines per block
@@ -619,7 +693,8 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     dim3 grid;
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
-    const int fuse = c->nranks == 1;
+    const bool inl = F::NRED > 0 && redctl_inline_allreduce(c, rc, F::NRED);
+    const int fuse = c->nranks == 1 || inl;
     TMaps<F::NIN> tm;
     if (tma) {
         for (int a = 0; a < F::NIN; ++a) KL_TRY(tmap_encode(c, &tm.m[a], f.in[a], nx, ny));
@@ -658,7 +733,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
 #undef KL_ST_LAUNCH
 #undef KL_ST_GEO
     c->stats.kernel_launches++;
-    if (F::NRED > 0) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
+    if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;
 }
 
@@ -673,13 +748,14 @@ inline int pw_grid(size_t nchunk) {
 template <class F, class Post>
 inline int launch_pointwise(Ctx *c, F f, size_t n, const Post &post) {
     RedCtl rc = redctl(c);
-    const int fuse = c->nranks == 1;
+    const bool inl = F::NRED > 0 && redctl_inline_allreduce(c, rc, F::NRED);
+    const int fuse = c->nranks == 1 || inl;
     if (n % 2 == 0)
         k_pointwise<F, 2, Post><<<pw_grid(n / 2), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
     else
         k_pointwise<F, 1, Post><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
     c->stats.kernel_launches++;
-    if (F::NRED > 0) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
+    if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;
 }
 

@@ -201,6 +201,7 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const
         block_sum<NR, kStencilThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         if (grid_sum<NR>(acc, rc, nb, bid, &s_flag)) {
+            if (rc.peer) peer_allreduce_block<NR>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
         }
     }

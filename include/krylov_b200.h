@@ -119,6 +119,8 @@ enum {
     KL_OPT_CHAIN = 12,        /* 1 (default): temporally blocked kernels -- several dependent operator applications
                                  (Chebyshev degree k, cbpr2 o A, A o cbpr2) in one pass over HBM; 0: one pass each */
     KL_OPT_STENCIL_ROWS = 13, /* grid lines per CTA of the temporally blocked kernels (0 = heuristic)       */
+    KL_OPT_INLINE_ALLREDUCE = 14, /* multi-GPU with peer memory: 1 (default) = the last block of a reducing kernel does
+                                 the NVLink all-reduce and the scalar recurrence itself; 0 = separate kernels  */
     KL_OPT_PEER = 10          /* multi-GPU: 1 = NVLink peer-memory all-reduce / halo push (default when the
                                  IPC mapping succeeded), 0 = NCCL collectives.  Set on all ranks alike. */
 };
