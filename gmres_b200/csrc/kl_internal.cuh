@@ -327,8 +327,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // rank pushes its sums into every rank's inbox with posted stores, raises a release flag carrying the sequence
 // number, waits for the P flags and adds the inbox in rank order -- identical bits on every rank.  Same
 // protocol, buffers and sequence counter as k_peer_allreduce (kl_core.cu), so both can be mixed in a stream.
+// (__noinline__: inlined, its spin loops raised the register count of the point-wise kernels from 80 to 106,
+// i.e. from 3 to 2 resident blocks per SM, and cost 40 % of their bandwidth on ONE GPU.)
 template <int K>
-__device__ __forceinline__ void peer_allreduce_block(const RedCtl &rc) {
+__device__ __noinline__ void peer_allreduce_block(const RedCtl &rc) {
     const PeerCtl &pc = *rc.peer;
     const int P = pc.nranks, rank = pc.rank, par = (int)(rc.seq & 1ull);
     for (int t = threadIdx.x; t < K * P; t += blockDim.x) {
