@@ -666,7 +666,7 @@ namespace kl {
 // the tail of a partially filled last wave is self-correcting (the remaining CTAs get the whole HBM
 // bandwidth), while few long CTAs load-balance badly: a "whole waves" geometry measured 8 % slower on the
 // 8-GPU strong-scaling case (2048 local lines), so the simple rule stays.  `resident` is unused for now.
-inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid) {
+inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid, int rows_opt = 0) {
     (void)resident;
     const long gx = (nx + strip - 1) / strip;
     if (gx > kMaxBlocks) return false;
@@ -674,6 +674,7 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     long rows = ((long)ny * gx + want - 1) / want;
     if (rows < 8) rows = 8;
     if (rows > 64) rows = 64;
+    if (rows_opt > 0) rows = rows_opt;     // KL_OPT_STENCIL_ROWS (tuning experiments)
     if (rows > ny) rows = ny;
     long gy = (ny + rows - 1) / rows;
     if (gx * gy > kMaxBlocks) {   // the deterministic reduction keeps one partial per CTA
@@ -712,7 +713,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
                 occ < 1)                                                                            \
                 occ = 4;                                                                            \
         }                                                                                           \
-        if (!stencil_geometry(nx, ny, strip, (long)occ * kNumSM, &g, &grid))                        \
+        if (!stencil_geometry(nx, ny, strip, (long)occ * kNumSM, &g, &grid, c->opt_stencil_rows))   \
             return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");           \
     }
 #define KL_ST_LAUNCH(OPK)                                                                           \
