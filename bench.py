@@ -10,6 +10,11 @@ row slabs (halo send/recv + scalar all-reduces).  At N=1 the JSON line also carr
 `extra` results for configs[2] (Chebyshev-preconditioned GMRES-MGSR(95), 4096^2),
 configs[1] (Householder GMRES(95), 1024^2) and configs[4] (BiCGSTAB, 8192^2/GPU).
 
+Bytes: `roofline` and `roofline_iter` use the bytes the kernels actually have to move (kl_get_stats /
+kl_get_profile, listed per kernel in DESIGN.md section 3): plain CG executes 64n B per iteration (the operator
+is applied twice instead of storing A p; SURVEY.md section 8d assumed 80n), PCG + cbpr2 80n, BiCGSTAB + cbpr2
+160n.  `roofline.traffic` is the DRAM traffic ncu measured for the dominant kernel (profiles/r01_traffic.json).
+
 Inputs are synthetic and deterministic (x_true = 1, b = A*1; no RNG), resident in HBM
 before the timed region; vectors (2.1 GB each) are far larger than the 126 MB L2, so no
 L2 flush is needed between iterations.  Timing: CUDA events on the launching stream

@@ -131,7 +131,10 @@ __device__ __forceinline__ double apply5c(double c, double l, double r, double d
     }
 }
 
-template <class C, int OPK>
+// MG: multi-GPU instantiation (lines above / below the slab come from the neighbours' halo buffers).  It is a
+// template parameter because the patch code in the level-0 path (global loads + ring stores in all six unrolled
+// phases) cost the single-GPU kernels 10-28 % when it was a run-time branch.
+template <class C, int OPK, bool MG>
 __global__ void __launch_bounds__(kChainThreads, C::MINB)
 k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_constant__ TMaps<C::NIN> tm) {
     if (c_in.skip()) return;
@@ -227,7 +230,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         // ---- level 0 -------------------------------------------------------
         {
             double raw[NIN][2];
-            if ((R < 0 && f.lo[0] != nullptr) || (R >= g.ny && f.hi[0] != nullptr)) {
+            if (MG && ((R < 0 && f.lo[0] != nullptr) || (R >= g.ny && f.hi[0] != nullptr))) {
                 // multi-GPU: this line belongs to a neighbour rank; TMA delivered zeros, take it from the halo
                 // buffer and patch the ring (every thread re-reads only its own column pair later)
 #pragma unroll
@@ -252,8 +255,6 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         // ---- levels 1..L ---------------------------------------------------
 #pragma unroll
         for (int l = 1; l <= L; ++l) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int sl_cu = (PH - l + 12) % 3;          // slot of line R-l in U[l-1]
             const int sl_up = (PH - l - 1 + 12) % 3;      // line R-l-1
             const int sl_dn = (PH - l + 1 + 12) % 3;      // line R-l+1
@@ -385,15 +386,17 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     TMaps<C::NIN> tm;
     for (int a = 0; a < C::NIN; ++a) KL_TRY(tmap_encode_box(c, &tm.m[a], f.in[a], nx, ny, D::BWP, RG::SR));
     constexpr size_t smem = RG::bytes;
-#define KL_CH_LAUNCH(OPK)                                                                              \
+#define KL_CH_LAUNCH1(OPK, MG)                                                                         \
     {                                                                                                  \
         static bool attr = false;                                                                      \
         if (!attr) {                                                                                   \
-            cudaFuncSetAttribute(k_chain_tma<C, OPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaFuncSetAttribute(k_chain_tma<C, OPK, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             attr = true;                                                                               \
         }                                                                                              \
-        k_chain_tma<C, OPK><<<grid, kChainThreads, smem, c->stream>>>(f, g, rc, tm);                   \
+        k_chain_tma<C, OPK, MG><<<grid, kChainThreads, smem, c->stream>>>(f, g, rc, tm);               \
     }
+#define KL_CH_LAUNCH(OPK)                                                                              \
+    if (f.lo[0] || f.hi[0]) KL_CH_LAUNCH1(OPK, true) else KL_CH_LAUNCH1(OPK, false)
     switch (op->kind) {
         case KL_OP_POISSON5: KL_CH_LAUNCH(KL_OP_POISSON5) break;
         case KL_OP_POISSON5_BRANCHY: KL_CH_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
@@ -401,6 +404,7 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
         default: return c->fail(KL_ERR_INVALID, "launch_chain: not a built-in operator");
     }
 #undef KL_CH_LAUNCH
+#undef KL_CH_LAUNCH1
     c->stats.kernel_launches++;
     // the post functor (scalar recurrences on the reduced sums) runs in its own one-warp kernel: the chain
     // kernels are not templated on it (each instantiation is 6 phases x L levels of code)
@@ -449,6 +453,48 @@ struct ChCheb : ChainBase<1, L_, 1, 1> {
         if (lv == L_ && out) {
             stg2(z + idx, u[0], u[1]);
             if (d_out) stg2(d_out + idx, cout[0][0], cout[0][1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (mode == 1) acc[0] = fma(u[e], u[e], acc[0]);
+                if (mode == 2) acc[0] = fma(r2[e], u[e], acc[0]);
+            }
+        }
+    }
+};
+
+// Continuation chunk for degrees 7..12: steps s0+1 .. s0+L from the stored iterate and direction.
+//   in[0] = z_{s0}, in[1] = d_{s0}, in[2] = r ;  level 0: u = z, d = d ;  level l as above ;  z = u_L
+// z and d are read with the CTA's halo lines, so the outputs must be other buffers than the inputs.
+template <int L_>
+struct ChChebCont : ChainBase<3, L_, 1, 1> {
+    static constexpr int SR = 2, NST = 6;                 // 12-line ring: keeps up to 6 lines behind the march
+    static constexpr int MINB = L_ <= 4 ? 3 : 2;          // 74 KB of ring per CTA: 3 CTAs per SM at most
+    double *z;
+    int mode;
+    double c1[L_], c2[L_];
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void level0(bool, size_t, const double (&raw)[3][2], double (&u)[2],
+                                           double (&cc)[1][2], double *) const {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            u[e] = raw[0][e];
+            cc[0][e] = raw[1][e];
+        }
+    }
+    template <class RAW>
+    __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+                                          const double (&cin)[1][2], RAW raw, const double (&)[1][2], double (&u)[2],
+                                          double (&cout)[1][2], double *acc) const {
+        const double2 rr = raw(2);
+        const double r2[2] = {rr.x, rr.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double d = fma(c1[lv - 1], cin[0][e], c2[lv - 1] * (r2[e] - au[e]));
+            u[e] = up[e] + d;
+            cout[0][e] = d;
+        }
+        if (lv == L_ && out) {
+            stg2(z + idx, u[0], u[1]);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (mode == 1) acc[0] = fma(u[e], u[e], acc[0]);

@@ -670,7 +670,11 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     (void)resident;
     const long gx = (nx + strip - 1) / strip;
     if (gx > kMaxBlocks) return false;
-    const long want = (long)kNumSM * 8;
+    // Wide grids (>= 32 strips): ~28 CTAs per SM.  A CTA lives ~100 us there, and the kernel ends with a ragged
+    // tail of about a third of that; on the 2048-line slab of the 8-GPU strong-scaling run 32-line CTAs (4224 CTAs)
+    // measured 3 % faster per iteration than 64-line ones, while below 32 lines the per-CTA overhead and the two
+    // halo lines per CTA cost more than the tail (scripts/slab_sweep.py).
+    const long want = (long)kNumSM * (gx >= 32 ? 28 : 8);
     long rows = ((long)ny * gx + want - 1) / want;
     if (rows < 8) rows = 8;
     if (rows > 64) rows = 64;

@@ -166,7 +166,10 @@ int pc_apply(Prob *P, const double *r, double *z, double *aux, double *aux2, int
         int s0 = 0;
         // ping-pong so that the final result lands in z: z_k = z if k odd else aux
         double *zb[2] = {z, aux};
-        const int kc = k < kChainMaxL ? k : kChainMaxL;
+        // degree <= 6: one chain ; 7..12: two balanced chains (the second continues from the stored z and d) ;
+        // above: a chain of 6 and one pass per remaining step
+        const bool two = k > kChainMaxL && k <= 2 * kChainMaxL;
+        const int kc = two ? (k + 1) / 2 : (k < kChainMaxL ? k : kChainMaxL);
         if (chain_ok(P, kc)) {
             // the first min(k, 6) steps in ONE pass over r (kl_chain_tma.cuh): 16n B instead of 40n B per step
             Halo H;
@@ -179,7 +182,7 @@ int pc_apply(Prob *P, const double *r, double *z, double *aux, double *aux2, int
                 c2s[s] = 2.0 * rho / delta;
                 rho_prev = rho;
             }
-            double *dst = (kc == k) ? z : zb[(k - kc) & 1];
+            double *dst = (kc == k) ? z : (two ? aux : zb[(k - kc) & 1]);
 #define KL_CC(LL)                                                                       \
     case LL: {                                                                          \
         ChCheb<LL> f;                                                                   \
@@ -197,6 +200,35 @@ int pc_apply(Prob *P, const double *r, double *z, double *aux, double *aux2, int
             }
 #undef KL_CC
             if (kc == k) return KL_OK;
+            if (two) {
+                // second chain: (z_kc, d_kc, r) -> z_k.  Inputs aux, aux2 ; output z.
+                const int kb = k - kc;
+                Halo H2;
+                const double *hv3[3] = {aux, aux2, r};
+                KL_TRY(halo_exchange_lines(P, hv3, 3, kb, &H2));
+                for (int s = 0; s < kb; ++s) {
+                    double rho = 1.0 / (2.0 * sigma - rho_prev);
+                    c1s[s] = rho * rho_prev;
+                    c2s[s] = 2.0 * rho / delta;
+                    rho_prev = rho;
+                }
+#define KL_CT(LL)                                                                       \
+    case LL: {                                                                          \
+        ChChebCont<LL> f;                                                               \
+        set_io(f, P, hv3, H2);                                                          \
+        set_gate(f, c, gated);                                                          \
+        f.z = z; f.mode = mode;                                                         \
+        for (int s = 0; s < LL; ++s) { f.c1[s] = c1s[s]; f.c2[s] = c2s[s]; }            \
+        if (mode != 0) { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, post)); }     \
+        else { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, NoPost{})); }           \
+    } break;
+                switch (kb) {
+                    KL_CT(1) KL_CT(2) KL_CT(3) KL_CT(4) KL_CT(5) KL_CT(6)
+                    default: return c->fail(KL_ERR_INVALID, "chebyshev chain length");
+                }
+#undef KL_CT
+                return KL_OK;
+            }
             s0 = kc;
         }
         for (int s = s0; s < k; ++s) {

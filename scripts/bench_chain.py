@@ -24,7 +24,7 @@ with torch.cuda.stream(st):
     r = torch.randn(n, dtype=torch.float64, device="cuda")
     z = torch.empty_like(r)
     out = {}
-    for k in (1, 2, 3, 4, 5, 6, 8):
+    for k in (1, 2, 3, 4, 5, 6, 8, 12):
         for chain in (1, 0):
             h.set_option(kl.KL_OPT_CHAIN, chain)
             h.set_output_buffer(z)

@@ -8,9 +8,9 @@ import gmres_b200 as kl
 nx = 16384
 h = kl.Handle(0)
 h.set_option(3, 0)
-for ny in (2048, 4096):
+for ny in (2048, 4096, 16384):
     b = h.apply(kl.stvec, torch.ones(nx * ny, dtype=torch.float64, device="cuda"), nx, ny)
-    for rows in (0, 16, 24, 32, 48, 64, 96, 128):
+    for rows in (0, 32, 64):
         h.set_option(kl.KL_OPT_STENCIL_ROWS, rows)
         h.set_option(4, 50)
         h.cg_omp(kl.stvec, b, 0.0, 10, nx=nx, ny=ny)

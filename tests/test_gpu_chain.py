@@ -37,7 +37,7 @@ def test_cheb_chain_bit_identical_to_stepwise(kl, h, nx, ny):
     rng = np.random.default_rng(nx * 7 + ny)
     r = rng.standard_normal(nx * ny)
     for op in (kl.stvec, kl.stv_poisson, kl.aniso(1.0, 0.01)):
-        for k in (1, 2, 3, 4, 5, 6, 7, 9):
+        for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13):   # <= 6 one chain, 7..12 two chains, 13 = chain of 6 + 7 passes
             zc = h.apply_precond(kl.cheb(k), op, r, (0.2, 8.2), nx, ny)
             zs = _no_chain(kl, h, lambda: h.apply_precond(kl.cheb(k), op, r, (0.2, 8.2), nx, ny))
             assert np.array_equal(zc, zs), (nx, ny, k, op.kind, np.abs(zc - zs).max())
