@@ -10,7 +10,7 @@
 //   K2  s = r - alpha ap' ; as = A s ; as.s, as.as              reads r,ap'      writes s,as    32n
 //   K3  x += alpha p' + omega s ; r = s - omega as ; r.r, r.r0  reads x,p',s,as,r0 writes x,r   56n
 //  cbpr2 (160n B): K1/K2 are temporally blocked chains (kl_chain_tma.cuh): direction update, cbpr2 and the
-//   operator in one pass (ChBiDir 56n, ChBiS 40n), K3 64n.  KL_OPT_CHAIN = 0 / multi GPU (184n B): K1/K2
+//   operator in one pass (ChBiDir 56n, ChBiS 40n), K3 64n.  KL_OPT_CHAIN = 0 (184n B): K1/K2
 //   produce z1 = cbpr2(p'), z2 = cbpr2(s) in one pass and a second stencil kernel applies the operator to
 //   z1/z2 carrying the dot products.
 // p and ap are ping-ponged because neighbouring thread blocks still read the old

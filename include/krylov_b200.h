@@ -154,7 +154,11 @@ int kl_vec_download(kl_handle_t h, double *h_dst, const double *d_src, size_t n)
 
 /* ---- operator / preconditioner application ------------------------------
  * call stvec(x, y, n)                      src/problems/poisson.f90:33
- * call cbpr2(A_x, r, z, aux, params, n)    src/preconds/chebyshev.f90:8       */
+ * call cbpr2(A_x, r, z, aux, params, n)    src/preconds/chebyshev.f90:8
+ * Host pointer mode: the vectors are copied in and out and the call returns when y / z is on the host.
+ * Device pointer mode: x / r and y / z (distinct buffers) are used in place and the call is stream-ordered
+ * (it returns after enqueueing; kl_synchronize or any later call on the handle's stream orders after it).
+ * KL_PC_CHEB of degree k <= 12 runs as one or two temporally blocked passes over HBM (KL_OPT_CHAIN).      */
 int kl_apply_operator(kl_handle_t h, const kl_operator_t *A_x, const double *x, double *y, int nx,
                       int ny);
 int kl_apply_precond(kl_handle_t h, const kl_precond_t *M_inv, const kl_operator_t *A_x,
