@@ -1,9 +1,13 @@
 // kl_chain_tma.cuh -- temporally blocked ("chained") marching stencil kernel (sm_100a).
 //
 // L dependent applications of the 5-point operator in ONE pass over HBM: the
-// degree-k Chebyshev preconditioner (k applications), cbpr2 o A and A o cbpr2
-// (GMRES / BiCGSTAB) read their inputs once and write their outputs once, no
-// matter how many operator applications lie in between.
+// degree-k Chebyshev preconditioner (k applications; ChCheb / ChChebCont below)
+// and BiCGSTAB's "update -> cbpr2 -> operator -> dot products" steps (ChBiDir,
+// ChBiS in kl_bicgstab.cu) read their inputs once and write their outputs once,
+// no matter how many operator applications lie in between.  Measured (8192^2,
+// DESIGN.md section 6): DRAM traffic = inputs + outputs (ncu), degree 4 in 441 us
+// against 1601 us for four passes; the kernel is issue-bound, not HBM-bound,
+// beyond L = 1 (~50 instructions per level and warp-line, 16 of them FP64).
 //
 // Geometry.  A CTA of 4 warps owns a strip of 4*(64-2H) columns, H = L rounded
 // up to even, and marches down `rows` grid lines.  Every WARP is independent: it
@@ -28,7 +32,12 @@
 // 0; levels >= 1 are forced to zero outside the domain (those points are not
 // unknowns).
 //
-// Chain functor contract (see ChCheb below and kl_bicgstab.cu / kl_gmres.cu):
+// Multi-GPU (template parameter MG): the L lines above / below the slab come from
+// the neighbours' halo buffers (kl_ops.cu halo_exchange_lines) and are patched
+// into the ring by the thread that reads them; the neighbours' lines are
+// recomputed redundantly level by level, so one exchange serves the whole chain.
+//
+// Chain functor contract (see ChCheb below and ChBiDir / ChBiS in kl_bicgstab.cu):
 //   NIN, L, NC, NRED               inputs, levels, carried values per point, reductions
 //   void init()
 //   void level0(bool out, size_t idx, const double (&raw)[NIN][2], double (&u)[2], double (&cc)[NC][2], double *acc)
