@@ -122,6 +122,7 @@ def load_library():
     L.kl_dense_matvec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.kl_lanczos.argtypes = [C.c_void_p, C.POINTER(kl_operator_t), C.c_int, C.c_int, C.c_int, _dp, _dp]
     L.kl_cheb_params_from_ritz.argtypes = [C.c_double, C.c_double, _dp]
+    L.kl_cheb_interval_from_ritz.argtypes = [C.c_double, C.c_int, _dp]
     L.kl_get_history.argtypes = [C.c_void_p, _dp, C.c_int, _ip]
     L.kl_get_stats.argtypes = [C.c_void_p, C.POINTER(kl_stats_t)]
     L.kl_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong), _dp]
@@ -484,6 +485,12 @@ class Handle:
         o, keep = A._c()
         self._chk(self._L.kl_lanczos(self._h, C.byref(o), nx, ny, steps, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def cheb_interval_from_ritz(self, theta_max: float, degree: int):
+        """params for cheb(degree): (b, b/ratio(degree)) with b = 1.025*theta_max (kl_cheb_interval_from_ritz)."""
+        out = (C.c_double * 2)()
+        self._chk(self._L.kl_cheb_interval_from_ritz(theta_max, int(degree), out))
+        return (out[0], out[1])
 
     def cheb_params_from_ritz(self, theta_min: float, theta_max: float):
         out = (C.c_double * 2)()

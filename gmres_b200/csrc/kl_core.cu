@@ -698,4 +698,17 @@ int kl_cheb_params_from_ritz(double theta_min, double theta_max, double params_o
     return KL_OK;
 }
 
+// Interval for the degree-k Chebyshev preconditioner (KL_PC_CHEB) from a Lanczos estimate: [b/ratio, b] with
+// b = 1.025 theta_max and a ratio that grows with the degree -- a degree-k polynomial can cover a wider part of
+// the spectrum.  The ratios are the best ones of the sweep in profiles/r01_cheb_sweep_2048.json (GMRES(95) and PCG
+// on the 2048^2 Poisson grid): 41 (the reference's cbpr2 policy) for k = 1, 100 for k = 2, 400 for k = 3..4,
+// 1000 above.  Host arithmetic only.
+int kl_cheb_interval_from_ritz(double theta_max, int degree, double params_out[2]) {
+    if (!params_out || !(theta_max > 0) || degree < 1) return KL_ERR_INVALID;
+    const double ratio = degree <= 1 ? 41.0 : (degree == 2 ? 100.0 : (degree <= 4 ? 400.0 : 1000.0));
+    params_out[0] = 1.025 * theta_max;
+    params_out[1] = params_out[0] / ratio;
+    return KL_OK;
+}
+
 }  // extern "C"

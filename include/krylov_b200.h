@@ -242,6 +242,9 @@ int kl_pbicgstab_omp(kl_handle_t h, const kl_operator_t *ax_op, const double *b,
 int kl_lanczos(kl_handle_t h, const kl_operator_t *A_x, int nx, int ny, int steps,
                double *theta_min, double *theta_max);
 int kl_cheb_params_from_ritz(double theta_min, double theta_max, double params_out[2]);
+/* interval [b/ratio(degree), b], b = 1.025*theta_max, for KL_PC_CHEB of the given degree (ratios from the
+ * measured sweep profiles/r01_cheb_sweep_2048.json: 41, 100, 400, 400, 1000, ...)                        */
+int kl_cheb_interval_from_ritz(double theta_max, int degree, double params_out[2]);
 
 /* ---- diagnostics of the last solver call --------------------------------- */
 /* residual estimate of every inner iteration across restarts (final_err for

@@ -51,7 +51,7 @@ for key in which:
     b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
     t0 = time.perf_counter()
     lo, hi = h.lanczos(kl.stvec, n, n, 30)
-    prm = (1.025 * hi, 1.025 * hi / 1000.0)
+    prm = h.cheb_interval_from_ritz(hi, k)      # [b/ratio(k), b], b = 1.025*theta_max (ratio 1000 for k >= 5)
     if solver.startswith("gmres"):
         r = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cheb(k), prm, nx=n, ny=n)
         its = (r.restart_out - 1) * m + r.n_out

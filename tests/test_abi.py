@@ -66,3 +66,16 @@ def test_cheb_params_policy(lib):
     lib.kl_cheb_params_from_ritz.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     assert lib.kl_cheb_params_from_ritz(0.01, 8.0, out) == 0
     assert out[0] == pytest.approx(8.2) and out[1] == pytest.approx(0.2)   # tests/test_poisson_mf.f90:38
+
+
+def test_cheb_interval_policy_is_host_arithmetic():
+    """kl_cheb_interval_from_ritz needs no GPU: [b/ratio(k), b], b = 1.025*theta_max, ratios 41/100/400/400/1000."""
+    import ctypes as C
+    from gmres_b200.api import load_library
+    L = load_library()
+    out = (C.c_double * 2)()
+    for k, ratio in ((1, 41.0), (2, 100.0), (3, 400.0), (4, 400.0), (6, 1000.0), (12, 1000.0)):
+        assert L.kl_cheb_interval_from_ritz(8.0, k, out) == 0
+        assert out[0] == 1.025 * 8.0 and out[1] == out[0] / ratio
+    assert L.kl_cheb_interval_from_ritz(-1.0, 2, out) < 0 and L.kl_cheb_interval_from_ritz(8.0, 0, out) < 0
+    assert L.kl_cheb_params_from_ritz(0.01, 8.0, out) == 0 and out[0] == 8.2 and abs(out[1] - 0.2) < 1e-15
