@@ -95,10 +95,16 @@ struct FCgDirX : StencilBase<2, 1> {
 //                                                                                  reads r,p    writes r'    24n
 // A p is never written to or read from HBM: five FP64 operations per point are cheaper than 16 bytes.  K2
 // reuses the halo lines K1 exchanged (r and p_old have not changed), so there is no second exchange.
+// Multi-GPU ("producer pushes", kCbPush in kl_internal.cuh): the CTAs that own the slab's first / last line also
+// store that line of the NEW vector into the neighbour ranks' halo slots, so the next iteration needs no halo
+// kernel; the all-reduce that ends the same kernel makes the lines visible before any consumer starts.
 struct FCgDirX2 : StencilBase<2, 1> {
+    static constexpr bool kPush = true;
     double *p_new, *x_new;     // x is ping-ponged like p and r: out-of-place streams reach a higher HBM efficiency
     const double *x;
     const double *S;
+    double *push_first, *push_last;   // neighbours' slots for p_new's first / last line (nullptr: none)
+    size_t last_off;                  // (ny_local - 1) * nx
     double beta, alpha_prev;
     __device__ __forceinline__ void init() {
         beta = S[S_BETA];
@@ -107,7 +113,7 @@ struct FCgDirX2 : StencilBase<2, 1> {
     __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
     template <int VEC>
     __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
-                                          const double (&au)[VEC], double *acc) const {
+                                          const double (&au)[VEC], double *acc, int edge) const {
         double vx[VEC];
         KL_LD(VEC, vx, x, idx)
 #pragma unroll
@@ -117,20 +123,32 @@ struct FCgDirX2 : StencilBase<2, 1> {
         }
         KL_ST(VEC, x_new, idx, vx)
         KL_ST(VEC, p_new, idx, cu)
+        if (edge) {
+            if ((edge & 1) && push_first) { KL_ST(VEC, push_first, idx, cu) }
+            if ((edge & 2) && push_last) { KL_ST(VEC, push_last, idx - last_off, cu) }
+            __threadfence_system();
+        }
     }
 };
+// kLateWait: under programmatic dependent launch K2 starts while K1 is still running.  Everything it touches
+// before its first store() -- r, p_old, their halo lines, beta, the gate -- is older than K1; alpha (K1's last
+// block) is read by late_init() after griddep_wait().
 struct FCgRUpdate : StencilBase<2, 1> {
+    static constexpr bool kPush = true;
+    static constexpr bool kLateWait = true;
     double *r_new;
     const double *S;
+    double *push_first, *push_last;   // neighbours' slots for r_new's first / last line
+    size_t last_off;
     double beta, alpha;
     __device__ __forceinline__ void init() {
         beta = S[S_BETA];      // still the beta K1 used: PostCgEnd replaces it only after this kernel's last block
-        alpha = S[S_ALPHA];
     }
+    __device__ __forceinline__ void late_init() { alpha = S[S_ALPHA]; }
     __device__ __forceinline__ double point(const double (&v)[2]) const { return fma(beta, v[1], v[0]); }
     template <int VEC>
     __device__ __forceinline__ void store(size_t idx, const double (&raw)[2][VEC], const double (&cu)[VEC],
-                                          const double (&au)[VEC], double *acc) const {
+                                          const double (&au)[VEC], double *acc, int edge) const {
         double rn[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -138,6 +156,11 @@ struct FCgRUpdate : StencilBase<2, 1> {
             acc[0] = fma(rn[v], rn[v], acc[0]);               // :131-133
         }
         KL_ST(VEC, r_new, idx, rn)
+        if (edge) {
+            if ((edge & 1) && push_first) { KL_ST(VEC, push_first, idx, rn) }
+            if ((edge & 2) && push_last) { KL_ST(VEC, push_last, idx - last_off, rn) }
+            __threadfence_system();
+        }
     }
 };
 
@@ -242,6 +265,15 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
         int m1 = -1;
         KL_CUDA(c, cudaMemcpyAsync(c->d_I + I_CONV_AT, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
+    // multi-GPU, peer memory: the producing kernels push their boundary lines (slot 0 = r, slot 1 = p, parity =
+    // iteration & 1); the lines of r0 = b and p0 = 0 are pushed here, the all-reduce of the dot product below is
+    // the barrier that orders them before the first K1 on every rank
+    const bool push = twice && comm_push_ok(c, P.nx) && c->opt_tma && P.nx >= 64;
+    if (push) {
+        const double *first[2] = {r, nullptr}, *last[2] = {r + (size_t)(P.nyl - 1) * P.nx, nullptr};
+        const int slots[2] = {0, 1};
+        KL_TRY(comm_push_lines(c, 2, first, last, slots, 0, P.nx));
+    }
     // rr = r.z  (z = M^-1 r for pcg, cg.f90:182 ; z = r otherwise)
     if (prec) {
         KL_TRY(pc_apply(&P, r, z, aux, aux2, 2, false, PostStoreRed{c->d_S, S_RR, 0}));
@@ -265,23 +297,39 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
             if (twice) {
                 Halo H;
                 const double *vecs[2] = {r, pold};
-                KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                const int it = done + k + 1, par_in = (it - 1) & 1, par_out = it & 1;
+                if (push) {
+                    for (int a = 0; a < 4; ++a) H.lo[a] = H.hi[a] = nullptr;
+                    comm_push_recv(c, par_in, 0, &H.lo[0], &H.hi[0]);
+                    comm_push_recv(c, par_in, 1, &H.lo[1], &H.hi[1]);
+                } else {
+                    KL_TRY(halo_exchange(&P, vecs, 2, &H));
+                }
                 {
                     ProfScope ps(c, 0, "cg_xdir_dot (stencil: x+=alpha_prev*p; p=r+beta*p; (A p).p)", 40.0 * n);
                     FCgDirX2 f;
                     set_io(f, &P, vecs, H);
                     set_gate(f, c, true);
                     f.p_new = pnew; f.x = x_cur; f.x_new = x_alt; f.S = c->d_S;
-                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgAlpha{c->d_S}));
+                    f.push_first = f.push_last = nullptr;
+                    f.last_off = (size_t)(P.nyl - 1) * P.nx;
+                    if (push) comm_push_send(c, par_out, 1, &f.push_first, &f.push_last);
+                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgAlpha{c->d_S}, true));
                     std::swap(x_cur, x_alt);
                 }
+#ifdef KL_TRACE
+                if (getenv("KL_TRACE_K1") && it == maxit) continue;    // debug: leave K1's time stamps in g_trace
+#endif
                 {
                     ProfScope ps(c, 1, "cg_apply_rupdate_dot (stencil: r-=alpha*A(r+beta*p); r.r)", 24.0 * n);
                     FCgRUpdate f;
                     set_io(f, &P, vecs, H);      // same halo lines: r and p_old are unchanged since K1
                     set_gate(f, c, true);
                     f.r_new = r_alt; f.S = c->d_S;
-                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}));
+                    f.push_first = f.push_last = nullptr;
+                    f.last_off = (size_t)(P.nyl - 1) * P.nx;
+                    if (push) comm_push_send(c, par_out, 0, &f.push_first, &f.push_last);
+                    KL_TRY(launch_stencil(c, &P.op, f, P.nx, P.nyl, PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 0}, true));
                 }
                 std::swap(r, r_alt);
                 z = r;
@@ -411,6 +459,13 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
 using namespace kl;
 
 extern "C" {
+
+#ifdef KL_TRACE
+// debug: time stamps of the CTAs of the last stencil kernel launched from this file (3 u64 per CTA + 1)
+int kl_debug_trace_cg(unsigned long long *out, int n) {
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int kl_cg(kl_handle_t h, const kl_operator_t *A, const double *b, double *x, int nx, int ny, double tol,
           int *iter, double *res) {

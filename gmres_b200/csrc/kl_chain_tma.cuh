@@ -349,7 +349,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         __shared__ int s_flag;
         block_sum<NR_, kChainThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        grid_sum<NR_>(acc, rc, nb, bid, &s_flag);
+        grid_sum<NR_, kChainThreads>(acc, rc, nb, bid, &s_flag, sm);
     }
 }
 
@@ -397,10 +397,10 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     constexpr size_t smem = RG::bytes;
 #define KL_CH_LAUNCH1(OPK, MG)                                                                         \
     {                                                                                                  \
-        static bool attr = false;                                                                      \
-        if (!attr) {                                                                                   \
+        static bool attr[kMaxDevices] = {};   /* the shared-memory opt-in is per device */             \
+        if (!attr[c->device % kMaxDevices]) {                                                          \
             cudaFuncSetAttribute(k_chain_tma<C, OPK, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            attr = true;                                                                               \
+            attr[c->device % kMaxDevices] = true;                                                      \
         }                                                                                              \
         k_chain_tma<C, OPK, MG><<<grid, kChainThreads, smem, c->stream>>>(f, g, rc, tm);               \
     }

@@ -1,5 +1,6 @@
 // kl_core.cu -- handle lifecycle, options, workspace, device vectors, NCCL plumbing.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,13 +29,15 @@ int ws_reserve(Ctx *c, size_t bytes) {
     return KL_OK;
 }
 
-// 2-D FP64 tensor map over an nx x ny grid (i fastest), box = 256 columns x kTmaSR lines, zero fill
-// outside the grid.  Descriptors are cached per (pointer, extents); cuTensorMapEncodeTiled is taken
-// from the driver through the runtime so that libcuda is not a link-time dependency.
-int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
+// 2-D FP64 tensor maps (zero fill outside the tensor).  Descriptors are cached per handle, keyed by
+// (base pointer, extents, k1, k2); cuTensorMapEncodeTiled is taken from the driver through the runtime so that
+// libcuda is not a link-time dependency.
+static int tmap_get(Ctx *c, CUtensorMap *out, const void *base, int key_nx, int key_ny, long long k1, long long k2,
+                    cuuint64_t dim0, cuuint64_t dim1, cuuint64_t row_pitch_bytes, cuuint32_t box0, cuuint32_t box1,
+                    CUtensorMapL2promotion l2, const char *what) {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     for (auto &e : c->tmaps)
-        if (e.base == base && e.nx == nx && e.ny == ny && e.k1 == 0 && e.k2 == 0) {
+        if (e.base == base && e.nx == key_nx && e.ny == key_ny && e.k1 == k1 && e.k2 == k2) {
             memcpy(out, e.blob, sizeof(CUtensorMap));
             return KL_OK;
         }
@@ -46,83 +49,41 @@ int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
         c->encode_fn = fn;
     }
     auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
-    cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
-    cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)kTmaBoxX, (cuuint32_t)kTmaSR};
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {row_pitch_bytes};
+    cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, what);
     if (c->tmaps.size() >= 256) c->tmaps.clear();
     Ctx::TmapEntry e;
-    e.base = base; e.nx = nx; e.ny = ny;
+    e.base = base; e.nx = key_nx; e.ny = key_ny; e.k1 = k1; e.k2 = k2;
     memcpy(e.blob, out, sizeof(CUtensorMap));
     c->tmaps.push_back(e);
     return KL_OK;
+}
+
+// nx x ny grid (i fastest), box = 256 columns x kTmaSR lines (k_stencil_tma)
+int tmap_encode(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny) {
+    return tmap_get(c, out, base, nx, ny, 0, 0, (cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nx * sizeof(double),
+                    kTmaBoxX, kTmaSR, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "cuTensorMapEncodeTiled failed");
 }
 
 // grid tensor map with an explicit box (chained stencil kernels, kl_chain_tma.cuh); key: k1 = box_x, k2 = box_y
 int tmap_encode_box(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny, int box_x, int box_y) {
-    for (auto &e : c->tmaps)
-        if (e.base == base && e.nx == nx && e.ny == ny && e.k1 == box_x && e.k2 == box_y) {
-            memcpy(out, e.blob, sizeof(CUtensorMap));
-            return KL_OK;
-        }
-    if (!c->encode_fn) {
-        cudaDriverEntryPointQueryResult q;
-        void *fn = nullptr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || !fn) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled entry point", e);
-        c->encode_fn = fn;
-    }
-    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
-    cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
-    cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)box_x, (cuuint32_t)box_y};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled (box) failed");
-    if (c->tmaps.size() >= 256) c->tmaps.clear();
-    Ctx::TmapEntry e;
-    e.base = base; e.nx = nx; e.ny = ny; e.k1 = box_x; e.k2 = box_y;
-    memcpy(e.blob, out, sizeof(CUtensorMap));
-    c->tmaps.push_back(e);
-    return KL_OK;
+    return tmap_get(c, out, base, nx, ny, box_x, box_y, (cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nx * sizeof(double),
+                    (cuuint32_t)box_x, (cuuint32_t)box_y, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    "cuTensorMapEncodeTiled (box) failed");
 }
 
+// Krylov basis V (n rows fastest, ncols_total columns, ld = ldv), box = 32*RM rows x nc columns (k_ts_tma).
+// key: the ny field carries -nc so that it cannot collide with a grid map
 static inline int ts_rm_host(int nc) { return nc <= 12 ? 8 : (nc <= 24 ? 4 : (nc <= 48 ? 2 : 1)); }
 int tmap_encode_v(Ctx *c, CUtensorMap *out, const double *V, size_t n, size_t ldv, int ncols_total, int nc) {
-    // key: (V, n, nc) -- ny field carries -nc so that it cannot collide with a grid map
-    for (auto &e : c->tmaps)
-        if (e.base == V && e.nx == (int)n && e.ny == -nc && e.k1 == (long long)ldv && e.k2 == ncols_total) {
-            memcpy(out, e.blob, sizeof(CUtensorMap));
-            return KL_OK;
-        }
-    if (!c->encode_fn) {
-        cudaDriverEntryPointQueryResult q;
-        void *fn = nullptr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || !fn) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled entry point", e);
-        c->encode_fn = fn;
-    }
-    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c->encode_fn);
-    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)ncols_total};
-    cuuint64_t strides[1] = {(cuuint64_t)ldv * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)(32 * ts_rm_host(nc)), (cuuint32_t)nc};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(V), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return c->fail(KL_ERR_CUDA, "cuTensorMapEncodeTiled (V) failed");
-    if (c->tmaps.size() >= 256) c->tmaps.clear();
-    Ctx::TmapEntry e;
-    e.base = V; e.nx = (int)n; e.ny = -nc; e.k1 = (long long)ldv; e.k2 = ncols_total;
-    memcpy(e.blob, out, sizeof(CUtensorMap));
-    c->tmaps.push_back(e);
-    return KL_OK;
+    return tmap_get(c, out, V, (int)n, -nc, (long long)ldv, ncols_total, (cuuint64_t)n, (cuuint64_t)ncols_total,
+                    (cuuint64_t)ldv * sizeof(double), (cuuint32_t)(32 * ts_rm_host(nc)), (cuuint32_t)nc,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "cuTensorMapEncodeTiled (V) failed");
 }
 
 void prof_reset(Ctx *c) {
@@ -238,35 +199,59 @@ static int nccl_load(std::string *err) {
 struct PeerPtrs {
     double *p[16];
 };
-__global__ void k_peer_allreduce(double *buf, const int count, const PeerPtrs pp, const int rank, const int P,
-                                 const unsigned long long seq, int *I) {
+__global__ void k_peer_allreduce(double *buf, const int count, PeerCtl *ctl, int *I) {
+    const PeerCtl &pc = *ctl;
+    const int rank = pc.rank, P = pc.nranks;
+    const unsigned long long seq = pc.ar_seq + 1ull;    // sequence of EXECUTED all-reduces (see PeerCtl)
     const int par = (int)(seq & 1ull);
     // push my values into every rank's inbox (including my own)
     for (int t = threadIdx.x; t < count * P; t += blockDim.x) {
         const int q = t / count, i = t - q * count;
-        pp.p[q][kCbArInbox + ((size_t)par * 16 + rank) * kArMax + i] = buf[i];
+        pc.p[q][kCbArInbox + ((size_t)par * 16 + rank) * kArMax + i] = buf[i];
     }
     __syncthreads();
     if (threadIdx.x < P) {
         __threadfence_system();
-        unsigned long long *fl = reinterpret_cast<unsigned long long *>(pp.p[threadIdx.x] + kCbArFlags);
+        unsigned long long *fl = reinterpret_cast<unsigned long long *>(pc.p[threadIdx.x] + kCbArFlags);
         st_release_sys(fl + par * 16 + rank, seq);
     }
     // wait for every rank's contribution
     if (threadIdx.x < P) {
-        const unsigned long long *fl = reinterpret_cast<const unsigned long long *>(pp.p[rank] + kCbArFlags);
+        const unsigned long long *fl = reinterpret_cast<const unsigned long long *>(pc.p[rank] + kCbArFlags);
         long long spins = 0;
         while (ld_acquire_sys(fl + par * 16 + threadIdx.x) < seq) {
             if (++spins > kSpinLimit) { I[I_BREAKDOWN] = 1; break; }
         }
     }
     __syncthreads();
-    const double *inbox = pp.p[rank] + kCbArInbox + (size_t)par * 16 * kArMax;
+    const double *inbox = pc.p[rank] + kCbArInbox + (size_t)par * 16 * kArMax;
     for (int i = threadIdx.x; i < count; i += blockDim.x) {
         double sum = 0.0;
         for (int r = 0; r < P; ++r) sum += __ldcg(inbox + (size_t)r * kArMax + i);
         buf[i] = sum;
     }
+    if (threadIdx.x == 0) ctl->ar_seq = seq;
+}
+
+// Boundary lines of up to four slab vectors stored straight into the neighbours' PUSH slots (kCbPush) -- the
+// set-up step of the "producer pushes" halo scheme (kl_cg.cu): no flags, the all-reduce of the next reducing
+// kernel in the stream is the barrier.  block b = 2*v + dir ; dir 0: my first `count` doubles go to rank-1's
+// hi slot, dir 1: my last ones to rank+1's lo slot.  src == nullptr pushes zeros.
+struct PushArgs {
+    const double *first[4], *last[4];
+    int slot[4];
+};
+__global__ void k_push_lines(const PeerCtl *ctl, const PushArgs a, const int parity, const int count) {
+    const int v = blockIdx.x >> 1, dir = blockIdx.x & 1;
+    const int nb = dir == 0 ? ctl->rank - 1 : ctl->rank + 1;
+    if (nb < 0 || nb >= ctl->nranks) return;
+    const double *src = dir == 0 ? a.first[v] : a.last[v];
+    double *dst = ctl->p[nb] + push_slot_off(parity, a.slot[v], 1 - dir);
+    for (int i = threadIdx.x * 2; i < count; i += blockDim.x * 2) {
+        double2 t = src ? *reinterpret_cast<const double2 *>(src + i) : make_double2(0.0, 0.0);
+        *reinterpret_cast<double2 *>(dst + i) = t;
+    }
+    __threadfence_system();
 }
 
 // block b = 2*v + dir: dir 0 sends my first line of vector v to rank-1 (its "hi" halo) and waits for
@@ -308,9 +293,8 @@ static PeerPtrs peer_ptrs(const Ctx *c) {
 
 int comm_allreduce(Ctx *c, double *d_buf, int count) {
     if (c->nranks == 1) return KL_OK;
-    if (c->peer_ok && count <= kArMax) {
-        ++c->ar_seq;
-        k_peer_allreduce<<<1, 256, 0, c->stream>>>(d_buf, count, peer_ptrs(c), c->rank, c->nranks, c->ar_seq, c->d_I);
+    if (c->peer_ok && c->d_peerctl && count <= kArMax) {
+        k_peer_allreduce<<<1, 256, 0, c->stream>>>(d_buf, count, c->d_peerctl, c->d_I);
         c->stats.kernel_launches++;
         return KL_OK;
     }
@@ -362,6 +346,31 @@ int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *
     return KL_OK;
 }
 
+// "Producer pushes" halo scheme: is it available (all ranks take the same decision)?  count = doubles per line.
+bool comm_push_ok(const Ctx *c, int count) {
+    return c->nranks > 1 && c->peer_ok && c->d_peerctl && c->opt_inline_ar && c->opt_push_halo &&
+           count <= kHaloNxCap && count % 2 == 0;
+}
+// where the neighbours' lines of (parity, slot) arrive in MY buffer: lo = rank-1's last line, hi = rank+1's first
+void comm_push_recv(const Ctx *c, int parity, int slot, const double **lo, const double **hi) {
+    *lo = c->rank > 0 ? c->cb_local + push_slot_off(parity, slot, 0) : nullptr;
+    *hi = c->rank < c->nranks - 1 ? c->cb_local + push_slot_off(parity, slot, 1) : nullptr;
+}
+// where MY first / last line of (parity, slot) has to be stored: rank-1's hi slot / rank+1's lo slot
+void comm_push_send(const Ctx *c, int parity, int slot, double **first_dst, double **last_dst) {
+    *first_dst = c->rank > 0 ? c->cb_peer[c->rank - 1] + push_slot_off(parity, slot, 1) : nullptr;
+    *last_dst = c->rank < c->nranks - 1 ? c->cb_peer[c->rank + 1] + push_slot_off(parity, slot, 0) : nullptr;
+}
+int comm_push_lines(Ctx *c, int nvec, const double *const *first, const double *const *last, const int *slots,
+                    int parity, int count) {
+    if (nvec < 1 || nvec > 4) return c->fail(KL_ERR_INVALID, "comm_push_lines: 1..4 vectors");
+    PushArgs a{};
+    for (int v = 0; v < nvec; ++v) { a.first[v] = first[v]; a.last[v] = last[v]; a.slot[v] = slots[v]; }
+    k_push_lines<<<2 * nvec, 256, 0, c->stream>>>(c->d_peerctl, a, parity, count);
+    c->stats.kernel_launches++;
+    return KL_OK;
+}
+
 // Map every rank's communication buffer into this process (CUDA IPC handles all-gathered over NCCL).
 static int peer_setup(Ctx *c) {
     c->peer_ok = false;
@@ -405,10 +414,13 @@ static int peer_setup(Ctx *c) {
         for (int r = 0; r < 16; ++r) pc.p[r] = c->cb_peer[r];
         pc.rank = c->rank;
         pc.nranks = c->nranks;
+        pc.ar_seq = 0ull;
         if (cudaMalloc(&c->d_peerctl, sizeof(PeerCtl)) == cudaSuccess)
             cudaMemcpy(c->d_peerctl, &pc, sizeof(PeerCtl), cudaMemcpyHostToDevice);
-        else { cudaGetLastError(); c->d_peerctl = nullptr; }
+        else { cudaGetLastError(); c->d_peerctl = nullptr; c->peer_ok = false; }
     }
+    // KL_OPT_PEER may re-enable the peer path later only if EVERY rank mapped every buffer
+    c->peer_mapped = c->peer_ok;
     return KL_OK;
 }
 
@@ -433,6 +445,13 @@ int kl_create(kl_handle_t *h, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return KL_ERR_CUDA;
     Ctx *c = new Ctx();
     c->device = device;
+    // experiment switches (same meaning as the options; options set later win)
+    if (const char *e = getenv("KL_PDL")) c->opt_pdl = atoi(e) != 0;
+    if (const char *e = getenv("KL_STENCIL_TAIL")) c->opt_stencil_tail = atoi(e);
+    if (const char *e = getenv("KL_STENCIL_STAGGER")) c->opt_stencil_stagger = atoi(e) != 0;
+    if (const char *e = getenv("KL_STENCIL_ROWS")) c->opt_stencil_rows = atoi(e);
+    if (const char *e = getenv("KL_PUSH_HALO")) c->opt_push_halo = atoi(e) != 0;
+    if (const char *e = getenv("KL_INLINE_ALLREDUCE")) c->opt_inline_ar = atoi(e) != 0;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_S, sizeof(double) * S_COUNT) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_I, sizeof(int) * I_COUNT) == cudaSuccess;
@@ -547,9 +566,13 @@ int kl_set_option(kl_handle_t h, int key, int value) {
             break;
         case KL_OPT_PEER:
             // all ranks must switch together; only meaningful before / between solves
-            if (value && !h->cb_local) return KL_ERR_INVALID;
-            h->peer_ok = value != 0 && h->cb_peer[0] != nullptr;
+            if (value && !h->peer_mapped) return KL_ERR_UNSUPPORTED;
+            h->peer_ok = value != 0;
             break;
+        case KL_OPT_PDL: h->opt_pdl = value != 0; break;
+        case KL_OPT_STENCIL_TAIL: h->opt_stencil_tail = value; break;
+        case KL_OPT_STENCIL_STAGGER: h->opt_stencil_stagger = value != 0; break;
+        case KL_OPT_PUSH_HALO: h->opt_push_halo = value != 0; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;
@@ -572,6 +595,10 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_STENCIL_ROWS: *value = h->opt_stencil_rows; break;
         case KL_OPT_REORTH_ETA: *value = h->opt_reorth_eta_permille; break;
         case KL_OPT_PEER: *value = h->peer_ok ? 1 : 0; break;
+        case KL_OPT_PDL: *value = h->opt_pdl; break;
+        case KL_OPT_STENCIL_TAIL: *value = h->opt_stencil_tail; break;
+        case KL_OPT_STENCIL_STAGGER: *value = h->opt_stencil_stagger; break;
+        case KL_OPT_PUSH_HALO: *value = h->opt_push_halo; break;
         default: return KL_ERR_INVALID;
     }
     return KL_OK;

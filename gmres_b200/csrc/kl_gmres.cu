@@ -243,7 +243,7 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
     __shared__ int s_flag;
     double accv[1] = {nacc};
     block_sum<1, kTsThreads>(accv, s_red);
-    if (grid_sum<1>(accv, rc, gridDim.x, blockIdx.x, &s_flag)) {
+    if (grid_sum<1, kTsThreads>(accv, rc, gridDim.x, blockIdx.x, &s_flag, s_red)) {
         if (fuse_givens && threadIdx.x < 32) givens_update_warp(G, j, sqrt(rc.red[0]), threadIdx.x, sm);
     }
 }
@@ -380,11 +380,11 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     CUtensorMap tm;
     KL_TRY(tmap_encode_v(c, &tm, V, n, ldv, ncols_total, nc));
     const size_t smem = ts_tma_smem(nc);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};   // the shared-memory opt-in is per device
+    if (!attr_done[c->device % kMaxDevices]) {
         cudaFuncSetAttribute(k_ts_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         cudaFuncSetAttribute(k_ts_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-        attr_done = true;
+        attr_done[c->device % kMaxDevices] = true;
     }
     const int RM = ts_rm(nc);
     size_t ntiles = (n + (size_t)kTsRB * RM - 1) / ((size_t)kTsRB * RM);

@@ -29,9 +29,10 @@ namespace kl {
 // limits
 // ------------------------------------------------------------------------
 constexpr int kMaxRed = 8;          // reductions per point-wise / stencil kernel
-constexpr int kMaxBlocks = 8192;    // upper bound on reducing-kernel grid size (partials leading dimension)
+constexpr int kMaxBlocks = 16384;    // upper bound on reducing-kernel grid size (partials leading dimension)
 constexpr int kMaxCols = 512;       // max restart length m+1 supported by the tall-skinny kernels
 constexpr int kNumSM = 148;
+constexpr int kMaxDevices = 16;      // per-device launch state (function attributes, occupancy)
 
 // device scalar block layout (doubles)
 enum SIdx {
@@ -64,19 +65,31 @@ constexpr size_t kCbArInbox = 0;                                        // [2][1
 constexpr size_t kCbArFlags = kCbArInbox + 2 * 16 * kArMax;             // [2][16] u64
 constexpr size_t kCbHaloFlags = kCbArFlags + 2 * 16;                    // [2][4 slots][2 dirs] u64
 constexpr size_t kCbHalo = kCbHaloFlags + 2 * 4 * 2;                    // [2][4][2][kHaloNxCap] doubles
-constexpr size_t kCbDoubles = kCbHalo + (size_t)2 * 4 * 2 * kHaloNxCap;
+// halo lines PUSHED BY THE PRODUCING KERNEL (edge CTAs of a stencil kernel store the first / last line of an
+// output vector straight into the neighbours' slots; the all-reduce that ends the same kernel is the barrier that
+// makes them visible before any consumer starts, so there is no halo kernel and no halo flag on that path)
+constexpr int kPushSlots = 4;
+constexpr size_t kCbPush = kCbHalo + (size_t)2 * 4 * 2 * kHaloNxCap;   // [2 parity][kPushSlots][2 dirs][kHaloNxCap]
+constexpr size_t kCbDoubles = kCbPush + (size_t)2 * kPushSlots * 2 * kHaloNxCap;
 constexpr long long kSpinLimit = 1ll << 27;   // ~seconds: a lost peer flags a breakdown instead of hanging
 struct PeerCtl {             // lives in device memory (RedCtl carries a pointer to it)
     double *p[16];           // every rank's communication buffer
     int rank, nranks;
+    // sequence number of the last EXECUTED all-reduce.  Device-resident on purpose: kernels that are gated off
+    // after convergence never take part in a collective, so a host-side counter would run ahead of the
+    // collectives that really happened and two executed all-reduces could share a parity slot with no
+    // cross-rank barrier between them.  Every rank executes the same collectives, so the counters agree.
+    unsigned long long ar_seq;
 };
+__host__ __device__ inline size_t push_slot_off(int parity, int slot, int dir) {
+    return kCbPush + (((size_t)parity * kPushSlots + slot) * 2 + dir) * kHaloNxCap;
+}
 
 struct RedCtl {
     double *partials;        // [grid * ld]
     unsigned int *counter;   // zero between kernels
     double *red;             // local sums destination
-    const PeerCtl *peer;     // != nullptr: the last block all-reduces `red` over NVLink before the post functor
-    unsigned long long seq;  // sequence number of that all-reduce
+    PeerCtl *peer;           // != nullptr: the last block all-reduces `red` over NVLink before the post functor
     int *I;                  // int block (breakdown flag for a lost peer)
 };
 
@@ -92,6 +105,12 @@ int comm_allreduce(Ctx *c, double *d_buf, int count);
 // (nullptr at the global boundary)
 int comm_halo_exchange(Ctx *c, const double *const *send_lo_rows, const double *const *send_hi_rows,
                        const double **lo_out, const double **hi_out, int nvec, int nx);
+// "producer pushes" halo scheme (kl_core.cu)
+bool comm_push_ok(const Ctx *c, int count);
+void comm_push_recv(const Ctx *c, int parity, int slot, const double **lo, const double **hi);
+void comm_push_send(const Ctx *c, int parity, int slot, double **first_dst, double **last_dst);
+int comm_push_lines(Ctx *c, int nvec, const double *const *first, const double *const *last, const int *slots,
+                    int parity, int count);
 
 }  // namespace kl
 
@@ -114,15 +133,20 @@ struct kl_context_s {
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
+    int opt_stencil_stagger = 1; // staggered tile heights (KL_OPT_STENCIL_STAGGER)
+    int opt_stencil_tail = -1;  // lines per CTA in the tapered tail (-1 auto, 0 off), KL_OPT_STENCIL_TAIL
+    int opt_pdl = 1;            // programmatic dependent launch between the fused CG kernels (KL_OPT_PDL)
     // comm
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
     // NVLink peer-memory collectives (one-shot all-reduce and halo push over IPC-mapped buffers)
     int opt_peer = 1;
     bool peer_ok = false;
+    bool peer_mapped = false;            // every rank mapped every peer buffer (peer_setup agreed)
+    int opt_push_halo = 1;               // producing kernels push their boundary lines (KL_OPT_PUSH_HALO)
     double *cb_local = nullptr;          // this rank's communication buffer
     double *cb_peer[16] = {};            // every rank's buffer mapped into this process (cb_peer[rank] = cb_local)
-    unsigned long long ar_seq = 0, halo_seq = 0;
+    unsigned long long halo_seq = 0;
     struct kl::PeerCtl *d_peerctl = nullptr;   // device copy of the peer pointers (inline all-reduce)
     int opt_inline_ar = 1;                     // all-reduce inside the reducing kernel's last block
     // device blocks
@@ -279,11 +303,14 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *smem /* K * NT
 
 // Grid-level deterministic reduction.  Every block calls this with its K block
 // sums valid in thread 0.  Returns true in ALL threads of the last block to
-// arrive, after red[0..K) holds the grid sums (summed over blocks in index
-// order by warp 0).  `nblocks` is the linear grid size, `bid` the linear id.
-template <int K>
+// arrive, after red[0..K) holds the grid sums.  The last block sums the partials
+// with all of its NT threads (thread t takes blocks t, t+NT, ... in increasing
+// order, four independent loads in flight), then combines the NT values in the
+// fixed order of block_sum: same launch configuration => same bits.  `nblocks`
+// is the linear grid size, `bid` the linear id, smem = K * NT/32 doubles.
+template <int K, int NT>
 __device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc, unsigned nblocks,
-                                         unsigned bid, int *s_flag) {
+                                         unsigned bid, int *s_flag, double *smem) {
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) rc.partials[(size_t)k * kMaxBlocks + bid] = v[k];
@@ -294,20 +321,27 @@ __device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc,
     __syncthreads();
     if (!*s_flag) return false;
     __threadfence();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+    double s[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const volatile double *p = rc.partials + (size_t)k * kMaxBlocks;
-            double s = 0.0;
-            for (unsigned b = lane; b < nblocks; b += 32) s += p[b];
-            s = warp_sum(s);
-            if (lane == 0) rc.red[k] = s;
+    for (int k = 0; k < K; ++k) {
+        const double *p = rc.partials + (size_t)k * kMaxBlocks;
+        double a = 0.0;
+        unsigned b = threadIdx.x;
+        for (; b + 3 * NT < nblocks; b += 4 * NT) {
+            const double t0 = __ldcg(p + b), t1 = __ldcg(p + b + NT), t2 = __ldcg(p + b + 2 * NT),
+                         t3 = __ldcg(p + b + 3 * NT);
+            a = ((a + t0) + t1) + t2;
+            a += t3;
         }
-        if (lane == 0) {
-            *rc.counter = 0u;
-            __threadfence();
-        }
+        for (; b < nblocks; b += NT) a += __ldcg(p + b);
+        s[k] = a;
+    }
+    block_sum<K, NT>(s, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rc.red[k] = s[k];
+        *rc.counter = 0u;
+        __threadfence();
     }
     __syncthreads();
     return true;
@@ -331,8 +365,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // i.e. from 3 to 2 resident blocks per SM, and cost 40 % of their bandwidth on ONE GPU.)
 template <int K>
 __device__ __noinline__ void peer_allreduce_block(const RedCtl &rc) {
-    const PeerCtl &pc = *rc.peer;
-    const int P = pc.nranks, rank = pc.rank, par = (int)(rc.seq & 1ull);
+    PeerCtl &pc = *rc.peer;
+    const unsigned long long seq = pc.ar_seq + 1ull;     // only this block touches it (kernels are stream-ordered)
+    const int P = pc.nranks, rank = pc.rank, par = (int)(seq & 1ull);
     for (int t = threadIdx.x; t < K * P; t += blockDim.x) {
         const int q = t / K, i = t - q * K;
         pc.p[q][kCbArInbox + ((size_t)par * 16 + rank) * kArMax + i] = rc.red[i];
@@ -341,10 +376,10 @@ __device__ __noinline__ void peer_allreduce_block(const RedCtl &rc) {
     if ((int)threadIdx.x < P) {
         __threadfence_system();
         unsigned long long *fl = reinterpret_cast<unsigned long long *>(pc.p[threadIdx.x] + kCbArFlags);
-        st_release_sys(fl + par * 16 + rank, rc.seq);
+        st_release_sys(fl + par * 16 + rank, seq);
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pc.p[rank] + kCbArFlags);
         long long spins = 0;
-        while (ld_acquire_sys(mine + par * 16 + threadIdx.x) < rc.seq) {
+        while (ld_acquire_sys(mine + par * 16 + threadIdx.x) < seq) {
             if (++spins > kSpinLimit) { rc.I[I_BREAKDOWN] = 1; break; }
         }
     }
@@ -355,8 +390,16 @@ __device__ __noinline__ void peer_allreduce_block(const RedCtl &rc) {
         for (int r = 0; r < P; ++r) sum += __ldcg(inbox + (size_t)r * kArMax + threadIdx.x);
         rc.red[threadIdx.x] = sum;
     }
+    if (threadIdx.x == 0) pc.ar_seq = seq;
     __syncthreads();
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialisation attribute
+// may start while its predecessor in the stream is still running; griddep_wait() blocks until the predecessor
+// has completed and its memory is visible, griddep_launch() allows the successor to be scheduled.  Both are
+// no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------
 // 5-point operator arithmetic.  OPK selects the reference's rounding order.
@@ -398,14 +441,40 @@ __device__ __forceinline__ double apply5(double c, double l, double r, double dn
 // Multi-GPU: lo/hi are the neighbour ranks' boundary lines of the NIN input
 // arrays (nullptr at the global boundary => zero Dirichlet).
 // ------------------------------------------------------------------------
+// CTA tiling in the march direction.  blockIdx.y < gy_main: the regular tiles, `rows` lines on average, with the
+// heights staggered in a period of four (h[0..3], prefix sums p[0..3], 4*rows per period) when stagger is on --
+// CTAs that start together then finish at four different times, later generations mix further, and the memory
+// system sees a steady stream instead of waves that start and drain in lockstep (measured time line:
+// profiles/r02_cta_timeline.md).  The CTAs behind them (scheduled last) own `rows_tail` lines each: small tiles
+// at the end of the grid shorten the kernel's tail.
 struct Geo {
     int nx, ny, rows;
+    int gy_main, rows_tail, main_end;
+    int h[4], p[4];
 };
+__device__ __forceinline__ void tile_lines(const Geo &g, int by, int &j0, int &j1) {
+    if (by < g.gy_main) {
+        j0 = (by >> 2) * (4 * g.rows) + g.p[by & 3];
+        j1 = min(j0 + g.h[by & 3], g.main_end);
+    } else {
+        j0 = g.main_end + (by - g.gy_main) * g.rows_tail;
+        j1 = min(j0 + g.rows_tail, g.ny);
+    }
+}
 
 template <int NIN_, int NRED_>
 struct StencilBase {
     static constexpr int NIN = NIN_;
     static constexpr int NRED = NRED_;
+    // kPush: store() takes a trailing `int edge` (bit 0: the points lie on the slab's first line, bit 1: on its
+    // last line) and may push those lines into the neighbour ranks' halo slots (multi-GPU, see kCbPush).
+    static constexpr bool kPush = false;
+    // kLateWait: nothing the kernel reads before its first store() is produced by the kernel launched just before
+    // it (inputs, halo lines, the gate and what init() reads are older), so under programmatic dependent launch
+    // the whole prologue -- barrier setup, the first TMA stages, the first lines of u -- overlaps the
+    // predecessor's tail; late_init() then reads the predecessor's scalars.
+    static constexpr bool kLateWait = false;
+    __device__ __forceinline__ void late_init() {}
     const double *in[NIN_];
     const double *lo[NIN_];
     const double *hi[NIN_];
@@ -434,9 +503,12 @@ constexpr int kPf = 2;   // prefetch distance in grid lines
 template <class F, int OPK, int VEC, class Post>
 __global__ void __launch_bounds__(kStencilThreads)
 k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post) {
+    griddep_wait();
+    griddep_launch();
     if (f_in.skip()) return;
     F f = f_in;
     f.init();
+    f.late_init();
     constexpr int NIN = F::NIN;
     constexpr int NRED = F::NRED;
     constexpr int NR = NRED > 0 ? NRED : 1;
@@ -445,8 +517,8 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
     const bool act = i0 < g.nx;
     const bool has_l = act && lane == 0 && i0 > 0;
     const bool has_r = act && lane == 31 && i0 + VEC < g.nx;
-    const int j0 = blockIdx.y * g.rows;
-    const int j1 = min(j0 + g.rows, g.ny);
+    int j0, j1;
+    tile_lines(g, blockIdx.y, j0, j1);
     double acc[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) acc[k] = 0.0;
@@ -535,7 +607,10 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
                 au[0] = apply5<OPK>(cu[0], l, cu[VEC - 1], dn[0], up[0], f.coef);
                 au[VEC - 1] = apply5<OPK>(cu[VEC - 1], cu[0], r, dn[VEC - 1], up[VEC - 1], f.coef);
             }
-            f.template store<VEC>((size_t)j * g.nx + i0, rawCu.c, cu, au, acc);
+            if constexpr (F::kPush)
+                f.template store<VEC>((size_t)j * g.nx + i0, rawCu.c, cu, au, acc, (j == 0 ? 1 : 0) | (j == g.ny - 1 ? 2 : 0));
+            else
+                f.template store<VEC>((size_t)j * g.nx + i0, rawCu.c, cu, au, acc);
         }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -553,7 +628,7 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
         __shared__ int s_flag;
         block_sum<NR, kStencilThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        if (grid_sum<NR>(acc, rc, nb, bid, &s_flag)) {
+        if (grid_sum<NR, kStencilThreads>(acc, rc, nb, bid, &s_flag, sm)) {
             if (rc.peer) peer_allreduce_block<NR>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
         }
@@ -569,6 +644,7 @@ constexpr int kPwThreads = 256;
 template <class F, int VEC, class Post>
 __global__ void __launch_bounds__(kPwThreads)
 k_pointwise(const F f_in, const size_t n, const RedCtl rc, const Post post, const int fuse_post) {
+    griddep_wait();
     if (f_in.skip()) return;
     F f = f_in;
     f.init();
@@ -585,7 +661,7 @@ k_pointwise(const F f_in, const size_t n, const RedCtl rc, const Post post, cons
         __shared__ double sm[(NRED > 0 ? NRED : 1) * (kPwThreads / 32)];
         __shared__ int s_flag;
         block_sum<(NRED > 0 ? NRED : 1), kPwThreads>(acc, sm);
-        if (grid_sum<(NRED > 0 ? NRED : 1)>(acc, rc, gridDim.x, blockIdx.x, &s_flag)) {
+        if (grid_sum<(NRED > 0 ? NRED : 1), kPwThreads>(acc, rc, gridDim.x, blockIdx.x, &s_flag, sm)) {
             if (rc.peer) peer_allreduce_block<(NRED > 0 ? NRED : 1)>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
         }
@@ -624,13 +700,12 @@ __global__ void k_post(const Post post, const int *flags, const int step, const 
 // ------------------------------------------------------------------------
 // launch helpers (host)
 // ------------------------------------------------------------------------
-inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED, nullptr, 0ull, c->d_I}; }
+inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED, nullptr, c->d_I}; }
 // Reducing kernel on several GPUs with NVLink peer memory: the kernel's last block does the all-reduce and runs
 // the post functor itself.  Returns true when that path is taken (then finish_reduction must not be called).
 inline bool redctl_inline_allreduce(Ctx *c, RedCtl &rc, int nred) {
     if (c->nranks == 1 || !c->peer_ok || !c->d_peerctl || !c->opt_inline_ar || nred > kArMax) return false;
     rc.peer = c->d_peerctl;
-    rc.seq = ++c->ar_seq;
     return true;
 }
 
@@ -666,8 +741,8 @@ namespace kl {
 // the tail of a partially filled last wave is self-correcting (the remaining CTAs get the whole HBM
 // bandwidth), while few long CTAs load-balance badly: a "whole waves" geometry measured 8 % slower on the
 // 8-GPU strong-scaling case (2048 local lines), so the simple rule stays.  `resident` is unused for now.
-inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid, int rows_opt = 0) {
-    (void)resident;
+inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid, int rows_opt = 0,
+                             int tail_opt = -1, int stagger = 1) {
     const long gx = (nx + strip - 1) / strip;
     if (gx > kMaxBlocks) return false;
     // Wide grids (>= 32 strips): ~28 CTAs per SM.  A CTA lives ~100 us there, and the kernel ends with a ragged
@@ -681,22 +756,58 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     if (rows_opt > 0) rows = rows_opt;     // KL_OPT_STENCIL_ROWS (tuning experiments)
     if (rows > ny) rows = ny;
     long gy = (ny + rows - 1) / rows;
-    if (gx * gy > kMaxBlocks) {   // the deterministic reduction keeps one partial per CTA
+    // tapered tail (KL_OPT_STENCIL_TAIL: -1 auto, 0 off, > 0 lines per tail CTA): the last half wave of CTAs gets
+    // tiles of a quarter of the height, so that the CTAs that finish last carry little work
+    long rt = tail_opt < 0 ? (rows >= 32 ? rows / 4 : 0) : tail_opt;
+    long tail_lines = 0, gy_tail = 0;
+    const bool multiwave = resident > 0 && gx * gy > 2 * resident;
+    if (rt > 0 && rt < rows && multiwave) {
+        long tl = (resident / 2 + gx - 1) / gx * rows;           // lines covered by half a wave of full tiles
+        if (tl > ny / 4) tl = ny / 4;
+        tail_lines = tl;
+    }
+    // staggered heights 5/8, 7/8, 9/8, 11/8 of `rows` (KL_OPT_STENCIL_STAGGER)
+    const bool stag = stagger && multiwave && rows >= 16;
+    long h[4], p[4];
+    for (int k = 0; k < 4; ++k) h[k] = stag ? rows * (5 + 2 * k) / 8 : rows;
+    h[3] = 4 * rows - h[0] - h[1] - h[2];
+    p[0] = 0;
+    for (int k = 1; k < 4; ++k) p[k] = p[k - 1] + h[k - 1];
+    auto count_main = [&](long main_end) {      // tiles needed to cover [0, main_end)
+        long full = main_end / (4 * rows), rem = main_end - full * 4 * rows, n = 4 * full;
+        for (int k = 0; k < 4 && rem > p[k]; ++k) ++n;
+        return n;
+    };
+    long main_end = ny - tail_lines;
+    long gy_main = count_main(main_end);
+    if (tail_lines > 0) gy_tail = (tail_lines + rt - 1) / rt;
+    if (gx * (gy_main + gy_tail) > kMaxBlocks) {   // the deterministic reduction keeps one partial per CTA
         const long max_gy = kMaxBlocks / gx;
         rows = (ny + max_gy - 1) / max_gy;
-        gy = (ny + rows - 1) / rows;
+        for (int k = 0; k < 4; ++k) { h[k] = rows; p[k] = k * rows; }
+        main_end = ny;
+        gy_main = (ny + rows - 1) / rows;
+        gy_tail = 0;
+        rt = 0;
     }
     g->nx = nx; g->ny = ny; g->rows = (int)rows;
-    *grid = dim3((unsigned)gx, (unsigned)gy);
+    g->gy_main = (int)gy_main;
+    g->rows_tail = (int)(gy_tail > 0 ? rt : rows);
+    g->main_end = (int)main_end;
+    for (int k = 0; k < 4; ++k) { g->h[k] = (int)h[k]; g->p[k] = (int)p[k]; }
+    *grid = dim3((unsigned)gx, (unsigned)(gy_main + gy_tail));
     return true;
 }
 
+// pdl: launch with the programmatic-stream-serialisation attribute (the kernel's own griddep_wait() orders it
+// after its predecessor; only for kernels that follow another k_stencil_tma / k_pointwise launch in the stream)
 template <class F, class Post>
-inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, const Post &post) {
+inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, const Post &post, bool pdl = false) {
     const int vec = (nx % 2 == 0) ? 2 : 1;
     const bool tma = c->opt_tma && vec == 2 && nx >= 64;
     const int strip = tma ? kTmaStrip : kStencilThreads * vec;
-    Geo g{nx, ny, 0};
+    Geo g{};
+    g.nx = nx; g.ny = ny;
     dim3 grid;
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
@@ -707,29 +818,42 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
         for (int a = 0; a < F::NIN; ++a) KL_TRY(tmap_encode(c, &tm.m[a], f.in[a], nx, ny));
     }
     constexpr size_t smem = tma_smem_bytes<F::NIN>();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kStencilThreads);
+    cfg.stream = c->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && c->opt_pdl) ? 1 : 0;
+    // the opt-in for > 48 KB of dynamic shared memory and the occupancy are per device (a process may hold
+    // handles on several devices)
 #define KL_ST_GEO(KERNEL, SMEM)                                                                     \
     {                                                                                               \
-        static int occ = 0;                                                                         \
-        if (!occ) {                                                                                 \
+        static int occ[kMaxDevices] = {};                                                           \
+        int &oc = occ[c->device % kMaxDevices];                                                     \
+        if (!oc) {                                                                                  \
             if (SMEM > 0)                                                                           \
                 cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, kStencilThreads, SMEM) != cudaSuccess || \
-                occ < 1)                                                                            \
-                occ = 4;                                                                            \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, KERNEL, kStencilThreads, SMEM) != cudaSuccess || \
+                oc < 1)                                                                             \
+                oc = 4;                                                                             \
         }                                                                                           \
-        if (!stencil_geometry(nx, ny, strip, (long)occ * kNumSM, &g, &grid, c->opt_stencil_rows))   \
+        if (!stencil_geometry(nx, ny, strip, (long)oc * kNumSM, &g, &grid, c->opt_stencil_rows, c->opt_stencil_tail, c->opt_stencil_stagger)) \
             return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");           \
+        cfg.gridDim = grid;                                                                         \
+        cfg.dynamicSmemBytes = SMEM;                                                                \
     }
 #define KL_ST_LAUNCH(OPK)                                                                           \
     if (tma) {                                                                                      \
         KL_ST_GEO((k_stencil_tma<F, OPK, Post>), smem)                                              \
-        k_stencil_tma<F, OPK, Post><<<grid, kStencilThreads, smem, c->stream>>>(f, g, rc, post, fuse, tm); \
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil_tma<F, OPK, Post>, f, g, rc, post, fuse, tm)); \
     } else if (vec == 2) {                                                                          \
         KL_ST_GEO((k_stencil<F, OPK, 2, Post>), 0)                                                  \
-        k_stencil<F, OPK, 2, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);  \
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, OPK, 2, Post>, f, g, rc, post, fuse));     \
     } else {                                                                                        \
         KL_ST_GEO((k_stencil<F, OPK, 1, Post>), 0)                                                  \
-        k_stencil<F, OPK, 1, Post><<<grid, kStencilThreads, 0, c->stream>>>(f, g, rc, post, fuse);  \
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, OPK, 1, Post>, f, g, rc, post, fuse));     \
     }
     switch (op->kind) {
         case KL_OP_POISSON5: KL_ST_LAUNCH(KL_OP_POISSON5) break;

@@ -60,13 +60,43 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         : "memory");
 }
 
+#ifdef KL_TRACE
+// debug build only: per-CTA (start, end, SM id) time stamps of the last k_stencil_tma launch of this translation unit
+static __device__ unsigned long long g_trace[3 * 16384 + 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+#endif
+
 template <class F, int OPK, class Post>
 __global__ void __launch_bounds__(kStencilThreads)
 k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post,
               const __grid_constant__ TMaps<F::NIN> tm) {
-    if (f_in.skip()) return;
+    // programmatic dependent launch (see griddep_wait): kLateWait functors run their whole prologue, the first TMA
+    // stages and the first lines of u before they need anything the preceding kernel produces
+#ifdef KL_TRACE
+    const unsigned long long t_start = gtimer();
+#endif
+    if (!F::kLateWait) griddep_wait();
+    griddep_launch();
+#ifdef KL_TRACE
+    const unsigned long long t_go = gtimer();
+#endif
+    if (f_in.skip()) {
+        if (F::kLateWait) griddep_wait();   // a grid completes only after its predecessor did
+        return;
+    }
     F f = f_in;
     f.init();
+    if (!F::kLateWait) f.late_init();
+    bool waited = !F::kLateWait;
     constexpr int NIN = F::NIN;
     constexpr int NRED = F::NRED;
     constexpr int NR = NRED > 0 ? NRED : 1;
@@ -85,8 +115,8 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const
     const bool outp = tid >= 1 && tid <= kStencilThreads - 2 && gi < g.nx;
     const bool has_l = lane == 0 && tid > 0;
     const bool has_r = lane == 31 && tid < kStencilThreads - 1;
-    const int j0 = blockIdx.y * g.rows;
-    const int j1 = min(j0 + g.rows, g.ny);
+    int j0, j1;
+    tile_lines(g, blockIdx.y, j0, j1);
     const int jstart = j0 - 1;
     const int nrows = j1 - j0 + 2;
     const int nst = (nrows + SR - 1) / SR;
@@ -168,11 +198,20 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const
                     double rt = __shfl_down_sync(0xffffffffu, cu[0], 1);
                     if (lane == 0) l = cl;
                     if (lane == 31) rt = cr;
+                    if (F::kLateWait && !waited) {
+                        griddep_wait();
+                        f.late_init();
+                        waited = true;
+                    }
                     if (outp) {
                         double au[VEC];
                         au[0] = apply5<OPK>(cu[0], l, cu[1], dn[0], up[0], f.coef);
                         au[1] = apply5<OPK>(cu[1], cu[0], rt, dn[1], up[1], f.coef);
-                        f.template store<VEC>((size_t)(r - 1) * g.nx + gi, rawCu, cu, au, acc);
+                        if constexpr (F::kPush)
+                            f.template store<VEC>((size_t)(r - 1) * g.nx + gi, rawCu, cu, au, acc,
+                                                  (r == 1 ? 1 : 0) | (r == g.ny ? 2 : 0));
+                        else
+                            f.template store<VEC>((size_t)(r - 1) * g.nx + gi, rawCu, cu, au, acc);
                     }
                 }
 #pragma unroll
@@ -195,14 +234,28 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const
             issue(k + NST);
         }
     }
+#ifdef KL_TRACE
+    if (threadIdx.x == 0) {
+        const unsigned b = blockIdx.y * gridDim.x + blockIdx.x;
+        if (b < 16384) {
+            g_trace[3 * b] = t_start;
+            g_trace[3 * b + 1] = gtimer();
+            g_trace[3 * b + 2] = ((unsigned long long)smid() << 48) | (t_go - t_start);
+        }
+    }
+#endif
     if (NRED > 0) {
         __shared__ double sm[NR * (kStencilThreads / 32)];
         __shared__ int s_flag;
         block_sum<NR, kStencilThreads>(acc, sm);
         const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        if (grid_sum<NR>(acc, rc, nb, bid, &s_flag)) {
+        if (F::kLateWait && !waited) griddep_wait();
+        if (grid_sum<NR, kStencilThreads>(acc, rc, nb, bid, &s_flag, sm)) {
             if (rc.peer) peer_allreduce_block<NR>(rc);
             if (fuse_post && threadIdx.x == 0) post.run();
+#ifdef KL_TRACE
+            if (threadIdx.x == 0) g_trace[3 * 16384] = gtimer();     // end of the last block's tail
+#endif
         }
     }
 }

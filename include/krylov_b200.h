@@ -121,6 +121,15 @@ enum {
     KL_OPT_STENCIL_ROWS = 13, /* grid lines per CTA of the temporally blocked kernels (0 = heuristic)       */
     KL_OPT_INLINE_ALLREDUCE = 14, /* multi-GPU with peer memory: 1 (default) = the last block of a reducing kernel does
                                  the NVLink all-reduce and the scalar recurrence itself; 0 = separate kernels  */
+    KL_OPT_PDL = 15,          /* 1 (default): the fused CG kernels are launched with programmatic dependent launch, so
+                                 the prologue of one overlaps the tail of the other; 0: plain stream order      */
+    KL_OPT_STENCIL_TAIL = 17, /* lines per CTA in the tapered tail of the stencil kernels' grids: -1 (default) = a quarter
+                                 of the regular tile height, 0 = off                                            */
+    KL_OPT_STENCIL_STAGGER = 18, /* 1 (default): CTA heights of the stencil kernels staggered (5/8 .. 11/8 of the mean) so
+                                 that CTAs do not start and drain in lockstep waves; 0: equal heights              */
+    KL_OPT_PUSH_HALO = 16,    /* multi-GPU with peer memory: 1 (default) = the kernel that PRODUCES a vector pushes its
+                                 boundary lines into the neighbours' halo slots (no halo kernel; the all-reduce that
+                                 ends the kernel is the barrier); 0 = separate halo push before every operator apply */
     KL_OPT_PEER = 10          /* multi-GPU: 1 = NVLink peer-memory all-reduce / halo push (default when the
                                  IPC mapping succeeded), 0 = NCCL collectives.  Set on all ranks alike. */
 };
