@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -114,9 +114,48 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw)}
+        # "under load": the samples taken while the GPU drew more than half of the highest power seen
+        load = sorted(c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "samples_under_load": len(load), "power_w_max": max(pw)}
+
+
+def workload_string(name, world):
+    """the same string in both arms (the driver compares config.workload of the b200 and the reference line)"""
+    w = WORKLOADS[name]
+    nx, ny = w["nx"], w["ny"] * (world if w["scaling"] == "weak" else 1)
+    pc = f" + {w['pc']}" if w["pc"] else ""
+    m = f"({w['m']})" if w["m"] else ""
+    op = f"anisotropic diffusion (eps {w['aniso'][0]:g}, {w['aniso'][1]:g})" if w.get("aniso") else "Poisson"
+    return (f"{w['solver']}{m}{pc}, {op} 2D 5-point matrix-free {nx}x{ny} ({nx * ny} unknowns), FP64, x_true=1, "
+            f"fixed K iterations (tol=0)")
+
+
+def history_parity(name, hist, r0):
+    """Residuals of the timed run against the committed history of the same workload (tests/golden/bench_history.json:
+    the CPU oracle's and the single-GPU run's first iterations) -- carries correctness into every bench line,
+    multi-GPU ones included.  max_rel = max |h_k/h'_k - 1|, max_norm = max |h_k - h'_k| / ||r_0||."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_history.json")) as f:
+            ref = json.load(f)[name]
+    except Exception:
+        return None
+    out = {}
+    for src in ("oracle", "gpu_n1"):
+        hr = ref.get(src)
+        if not hr:
+            continue
+        k = min(len(hr), len(hist))
+        if k == 0:
+            continue
+        rel = max(abs(hist[i] / hr[i] - 1.0) for i in range(k))
+        nrm = max(abs(hist[i] - hr[i]) for i in range(k)) / r0
+        out[src] = {"max_rel": rel, "max_norm": nrm, "iterations_compared": k}
+    if not out:
+        return None
+    best = out.get("oracle") or out.get("gpu_n1")
+    return {"max_rel": best["max_rel"], "max_norm": best["max_norm"], "iterations_compared": best["iterations_compared"],
+            "against": ref.get("source", ""), "detail": out}
 
 
 def make_ops(kl, w):
@@ -202,18 +241,20 @@ def gpu_arm(args):
         m = w["m"] or 1
         steps_eff = max(m, (steps // m) * m) if w["m"] else steps
         warm_eff = max(m, (warmup // m) * m) if w["m"] else max(warmup, 3)
-        run_gpu_solver(kl, h, w, b, nx, ny, warm_eff)                    # warm-up (untimed)
-        barrier()
         smp = ClockSampler(local)
         if rank == 0:
-            smp.start()
+            smp.start()          # 20 ms period, started before the warm-up so that the short timed region is covered
+        run_gpu_solver(kl, h, w, b, nx, ny, warm_eff)                    # warm-up (untimed)
+        barrier()
         r = run_gpu_solver(kl, h, w, b, nx, ny, steps_eff)               # timed: events inside the library
         barrier()
         clocks = smp.stop() if rank == 0 else None
         ms = max_over_ranks(r.stats["solve_ms"])
         its = r.stats["iterations"]
         launches = r.stats["kernel_launches"]
-        out = dict(workload=name, iterations=its, ms=ms, ms_per_step=ms / max(its, 1),
+        r0 = 1.0 if w["m"] else float(np.sqrt(4.0 * nx + 8.0)) if (nx == ny and not w.get("aniso")) else None
+        parity = history_parity(name, [float(v) for v in r.history], r0) if r0 else None
+        out = dict(workload=name, iterations=its, ms=ms, ms_per_step=ms / max(its, 1), parity=parity,
                    its_per_s=its / (ms * 1e-3), launches=int(launches), clocks=clocks,
                    bytes_per_iter=r.stats["algorithmic_bytes"] / max(its, 1) * world,
                    n_unknowns=nx * ny, nx=nx, ny=ny)
@@ -267,12 +308,26 @@ def gpu_arm(args):
             barrier()
             wall = max_over_ranks(time.perf_counter() - t0)
             tot_ms = max_over_ranks(r2.stats["total_ms"])
+            # the same call with PAGEABLE host arrays (what a Fortran `allocate` gives the drivers)
+            pageable = None
+            try:
+                bp = np.array(bn, copy=True)
+                h.set_output_buffer(np.empty_like(bp))
+                barrier()
+                r3 = run_gpu_solver(kl, h, w, bp, nx, ny, steps_eff)
+                barrier()
+                pageable = r3.stats["iterations"] / (max_over_ranks(r3.stats["total_ms"]) * 1e-3)
+                del bp
+            except Exception as ex:  # pragma: no cover
+                pageable = str(ex)[:100]
             out["e2e"] = dict(value=r2.stats["iterations"] / (tot_ms * 1e-3), unit="iterations/s",
+                              value_pageable_host=pageable,
                               h2d_bytes_per_step=r2.stats["h2d_bytes"] * world / max(r2.stats["iterations"], 1),
                               d2h_bytes_per_step=r2.stats["d2h_bytes"] * world / max(r2.stats["iterations"], 1),
                               total_ms=tot_ms, wall_ms=wall * 1e3,
-                              note="one solver call of K iterations through the C ABI with host buffers "
-                                   "(b uploaded, x downloaded once per call; device event time incl. copies)")
+                              note="one solver call of K iterations through the C ABI with pinned host buffers "
+                                   "(b uploaded, x downloaded once per call; device event time incl. copies); "
+                                   "value_pageable_host = the same with ordinary (pageable) host arrays")
         return out
 
     primary = measure(args.workload, args.steps, args.warmup, True, True)
@@ -285,7 +340,7 @@ def gpu_arm(args):
             try:
                 e = measure(name, st, st if WORKLOADS[name]["m"] else 3, False, True)
                 extras[name] = {k: e[k] for k in ("iterations", "ms_per_step", "its_per_s", "launches",
-                                                    "roofline_iter", "kernels") if k in e}
+                                                    "roofline_iter", "kernels", "parity") if k in e}
             except Exception as ex:  # pragma: no cover
                 extras[name] = {"error": str(ex)[:200]}
 
@@ -300,12 +355,17 @@ def gpu_arm(args):
             "n_gpus": world, "steps": primary["iterations"], "warmup": args.warmup,
             "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (x_true=1, b=A*1, no RNG)",
-            "config": {"workload": f"{w['solver']} Poisson 2D 5-point {primary['nx']}x{primary['ny']} "
-                                   f"({primary['n_unknowns']} unknowns), tol=0 (fixed K iterations)",
+            "config": {"workload": workload_string(args.workload, world),
                        "name": args.workload, "partition": f"row-slab x{world}",
                        "comm": ("none" if world == 1 else ("nvlink-peer-memory (IPC) all-reduce + halo push"
                                                             if h.get_option(10) else "nccl send/recv + allreduce")),
-                       "l2": "inputs larger than L2 (no flush needed)", "bytes_per_iteration": primary["bytes_per_iter"]},
+                       "l2": "inputs larger than L2 (no flush needed)", "bytes_per_iteration": primary["bytes_per_iter"],
+                       "roofline_iter_frac": primary["roofline_iter"]["frac"],
+                       "parity": primary.get("parity"),
+                       "extras": {k: {"its_per_s": round(v["its_per_s"], 2), "ms_per_step": round(v["ms_per_step"], 5),
+                                      "roofline_iter_frac": round(v["roofline_iter"]["frac"], 4),
+                                      "parity_max_rel": (v.get("parity") or {}).get("max_rel")}
+                                  for k, v in extras.items() if "its_per_s" in v}},
             "clocks": primary["clocks"], "gpu_launches": primary["launches"],
             "roofline": primary.get("roofline"), "roofline_iter": primary["roofline_iter"],
             "kernels": primary.get("kernels"), "e2e": primary.get("e2e"),
@@ -317,14 +377,16 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(workload, budget_s=20.0, threads=None):
-    """Time the oracle (C/OpenMP restatement of the reference's *_omp routine) on the host."""
+def cpu_baseline(workload, budget_s=20.0, threads=None, with_six=True):
+    """Time the oracle (C/OpenMP restatement of the reference's *_omp routine) on the host cores of this box.
+    Built here with the reference's own flags (-O3 -fopenmp -march=native -funroll-loops, CMakeLists.txt:5).
+    `value` = all host cores; `value_6_threads` = the reference drivers' own setting (tests/test_cg.f90:25)."""
     import numpy as np
     from oracle import oracle as ko
 
+    so = ko.build_native()
     w = WORKLOADS[workload]
     cores = threads or os.cpu_count()
-    ko.set_threads(cores)
     ns = w["nx"]
     n = ns * ns
     A = ko.stvec_fn()
@@ -347,19 +409,30 @@ def cpu_baseline(workload, budget_s=20.0, threads=None):
             ko.gmres_hh(A, b, iters, 0.0, None, max_stages=1, skip_verr=True, history_cap=1)
         return time.perf_counter() - t0
 
-    # calibrate: a short run (setup + i0 iterations), then a longer one; rate from the difference
-    i0 = 2
-    t_short = run(i0)
-    per_it = max(t_short / (i0 + 2), 1e-4)
-    i1 = int(min(max((budget_s * 0.6) / per_it, i0 + 3), 400))
-    if w["m"]:
-        i1 = min(i1, w["m"])
-    t_long = run(i1)
-    rate = (i1 - i0) / max(t_long - t_short, 1e-9)
-    return {"value": rate, "unit": "iterations/s", "cores": cores, "kind": "port",
-            "sample": f"{w['solver']} on {ns}x{ns}: ({i1}-{i0}) iterations, time difference of two runs "
-                      f"({t_long:.2f}s - {t_short:.2f}s) so that allocation/first-touch cancels; "
-                      f"oracle/krylov_oracle.c, gcc -O3 -fopenmp, OMP threads = {cores}"}
+    def rate(nthreads, budget):
+        # a short run (setup + i0 iterations), then a longer one; rate from the difference
+        ko.set_threads(nthreads)
+        i0 = 2
+        t_short = run(i0)
+        per_it = max(t_short / (i0 + 2), 1e-4)
+        i1 = int(min(max((budget * 0.6) / per_it, i0 + 3), 400))
+        if w["m"]:
+            i1 = min(i1, w["m"])
+        t_long = run(i1)
+        return (i1 - i0) / max(t_long - t_short, 1e-9), i0, i1, t_short, t_long
+
+    r_all, i0, i1, t_short, t_long = rate(cores, budget_s * (0.6 if with_six else 1.0))
+    out = {"value": r_all, "unit": "iterations/s", "cores": cores, "kind": "port",
+           "sample": f"{w['solver']} on {ns}x{ns}: ({i1}-{i0}) iterations, time difference of two runs "
+                     f"({t_long:.2f}s - {t_short:.2f}s) so that allocation/first-touch cancels; "
+                     f"oracle/krylov_oracle.c, gcc -O3 -fopenmp -march=native -funroll-loops built on this box "
+                     f"({os.path.relpath(so, ROOT)}), OMP threads = {cores}"}
+    if with_six and cores > 6:
+        r6, j0, j1, _, _ = rate(6, budget_s * 0.4)
+        out["value_6_threads"] = r6
+        out["sample"] += f"; value_6_threads: the reference drivers' own 6 threads (tests/test_cg.f90:25), ({j1}-{j0}) iterations"
+    ko.set_threads(1)
+    return out
 
 
 def reference_arm(args):
@@ -374,7 +447,7 @@ def reference_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
         "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (x_true=1, b=A*1, no RNG)",
-        "config": {"workload": f"{w['solver']} Poisson 2D 5-point {w['nx']}x{w['ny']}", "name": args.workload,
+        "config": {"workload": workload_string(args.workload, world), "name": args.workload,
                    "note": "reference is Fortran; no Fortran compiler on this box: C/OpenMP restatement "
                            "(oracle/) of the same routine on all host cores"},
         "cpu_baseline": cb,

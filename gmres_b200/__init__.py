@@ -13,6 +13,7 @@ fails loudly otherwise.
     r = h.gmres_mgsr_omp(kl.stvec, b, 95, 1e-8, kl.cbpr2, (8.2, 0.2))
     r.x, r.final_err, r.v_err, r.n_out, r.restart_out       # the reference's outputs
 """
+from . import api  # noqa: F401
 from .api import (  # noqa: F401
     Handle,
     KrylovError,

@@ -168,14 +168,38 @@ class Operator:
 
 @dataclass(frozen=True)
 class Precond:
-    """procedure(precond) -- src/interfaces.f90:19-28."""
+    """procedure(precond) -- src/interfaces.f90:19-28.
+
+    KL_PC_USER: `fn(A_x, d_r, d_z, d_aux, params, nx, ny_local, stream)` mirrors the reference's
+    `subroutine precond(A_x, r, z, aux, params, n)`: A_x is the solver's operator (an opaque
+    `const kl_operator_t *` that can be handed to kl_apply_operator), d_r / d_z / d_aux are device pointers
+    (aux is the solver's scratch vector, lent to the preconditioner as in gmres_mgsr.f90:302,337), params the
+    solver's params array.  Enqueue-only on `stream`; it must not synchronise."""
     kind: int
     degree: int = 0
+    fn: Optional[object] = None
 
     def _c(self):
         p = kl_precond_t()
         p.kind, p.degree = self.kind, self.degree
-        return p
+        keep = None
+        if self.kind == KL_PC_USER:
+            f = self.fn
+            if f is None:
+                raise KrylovError("Precond(KL_PC_USER) needs fn")
+
+            def tramp(h, a_x, user, d_r, d_z, d_aux, params, nparams, nx, nyl, stream):
+                try:
+                    f(a_x, d_r, d_z, d_aux, [params[i] for i in range(nparams)], nx, nyl, stream)
+                    return 0
+                except Exception:  # pragma: no cover
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+
+            keep = PRECOND_FN(tramp)
+            p.fn = keep
+        return p, keep
 
 
 stvec = Operator(KL_OP_POISSON5)                 # poisson::stvec        src/problems/poisson.f90:33
@@ -230,6 +254,8 @@ class Handle:
                               "(this library has no CPU path)")
         self.device = int(device)
         self.rank, self.nranks = 0, 1
+        self._user_stream = stream is not None     # an explicitly chosen stream is never rebound
+        self._bound_stream = None
         if stream is not None:
             self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream)))
 
@@ -263,7 +289,23 @@ class Handle:
         self.set_option(KL_OPT_ORTHO, mode)
 
     def set_stream(self, stream: Optional[int]):
+        """Run on an existing CUDA stream (None: the handle's own stream).  With an explicit stream the caller
+        orders the handle's work against the producers / consumers of device-resident vectors."""
         self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream or 0)))
+        self._user_stream = stream is not None
+        self._bound_stream = None
+
+    def _bind_torch_stream(self):
+        """Device-pointer mode: enqueue on torch's CURRENT stream, so that the library's kernels are ordered after
+        whatever produced the input tensors and before whatever consumes (or frees) the outputs.  The handle's
+        own stream is cudaStreamNonBlocking and would not synchronise with torch's streams at all."""
+        if self._user_stream:
+            return
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1     # 0 = legacy default stream = cudaStreamLegacy (0x1)
+        if s != self._bound_stream:
+            self._chk(self._L.kl_set_stream(self._h, C.c_void_p(s)))
+            self._bound_stream = s
 
     def synchronize(self):
         self._chk(self._L.kl_synchronize(self._h))
@@ -315,6 +357,7 @@ class Handle:
             import torch
             assert a.dtype == torch.float64 and a.is_contiguous()
             self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_DEVICE))
+            self._bind_torch_stream()
             return a, C.c_void_p(a.data_ptr()), True
         arr = np.ascontiguousarray(a, dtype=np.float64)
         self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_HOST))
@@ -361,7 +404,7 @@ class Handle:
         ra, rp, dev = self._in(r)
         z, zp = self._out_like(ra, dev)
         o, keep = A._c()
-        p = M._c()
+        p, keep_p = M._c()
         pr = np.ascontiguousarray(params, dtype=np.float64)
         self._chk(self._L.kl_apply_precond(self._h, C.byref(p), C.byref(o), rp, zp,
                                            pr.ctypes.data_as(_dp), pr.size, nx, ny))
@@ -379,7 +422,7 @@ class Handle:
         args = [self._h, C.byref(o), bp, xp, nx, ny, int(m), float(tol), fe.ctypes.data_as(_dp),
                 ve.ctypes.data_as(_dp), C.byref(n_out), C.byref(rs)]
         if with_pc:
-            p = (M or no_precond)._c()
+            p, keep_p = (M or no_precond)._c()
             pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
             args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
         rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
@@ -452,7 +495,7 @@ class Handle:
         o, keep = A._c()
         args = [self._h, C.byref(o), bp, xp, nx, ny, float(tol), C.byref(itc), C.byref(res)]
         if with_pc:
-            p = (M or no_precond)._c()
+            p, keep_p = (M or no_precond)._c()
             pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
             args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
         rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))

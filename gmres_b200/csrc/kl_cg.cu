@@ -289,9 +289,10 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     double *pold = p0, *pnew = p1;
     int done = 0, polls = 0;
     int status = KL_NOT_CONVERGED;
-    while (done < maxit) {
-        int batch = c->opt_check_every;
-        if (batch > maxit - done) batch = maxit - done;
+    // `count` iterations starting after iteration `done0`.  The buffer roles (r / r_alt, x_cur / x_alt, p_old / p_new)
+    // alternate with period two, so an even batch leaves them as it found them and can be replayed as a CUDA graph.
+    auto enqueue_iterations = [&](const int done0, const int batch) -> int {
+        const int done = done0;
         for (int k = 0; k < batch; ++k) {
             // ---- K1
             if (twice) {
@@ -406,6 +407,40 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
                                 PostCgEnd{c->d_S, c->d_I, c->d_hist, c->hist_cap, 1}));
             }
             double *t = pold; pold = pnew; pnew = t;
+        }
+        return KL_OK;
+    };
+    const bool use_graph = c->opt_use_graph && !c->opt_profile && c->nranks == 1 && fused &&
+                           (P.pc.kind == KL_PC_NONE || P.pc.kind == KL_PC_CBPR2 || P.pc.kind == KL_PC_CHEB);
+    while (done < maxit) {
+        int batch = c->opt_check_every;
+        if (batch > maxit - done) batch = maxit - done;
+        Ctx::GraphEntry *ge = nullptr;
+        if (use_graph && batch % 2 == 0 && done % 2 == 0) {
+            GraphKey gk;
+            gk.add('C').add(nx).add(ny).add(batch).add(P.op.kind).add(P.op.eps_x).add(P.op.eps_y).add(P.pc.kind)
+                .add(P.pc.degree).add(P.params).add(c->opt_tma).add(c->opt_chain).add(c->opt_stencil_rows)
+                .add(c->opt_stencil_tail).add(c->opt_stencil_stagger).add(c->opt_pdl).add(c->ws).add(dx).add(r).add(pold);
+            ge = graph_find(c, gk.s);
+            if (!ge && polls >= 1) {     // the first batch of a handle's first solve runs eagerly
+                const long long l0 = c->stats.kernel_launches;
+                KL_TRY(graph_begin(c));
+                const int rc = enqueue_iterations(done, batch);
+                if (rc < 0) {
+                    Ctx::GraphEntry *dummy = nullptr;
+                    graph_end(c, std::string(), 0.0, 0, &dummy);
+                    graph_clear(c);
+                    return rc;
+                }
+                KL_TRY(graph_end(c, gk.s, 0.0, c->stats.kernel_launches - l0, &ge));
+                c->stats.kernel_launches = l0;
+            }
+        }
+        if (ge) {
+            KL_CUDA(c, cudaGraphLaunch(ge->exec, c->stream));
+            c->stats.kernel_launches += ge->launches;
+        } else {
+            KL_TRY(enqueue_iterations(done, batch));
         }
         done += batch;
         KL_TRY(read_back(c));

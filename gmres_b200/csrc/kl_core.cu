@@ -12,8 +12,56 @@
 
 namespace kl {
 
+Ctx::GraphEntry *graph_find(Ctx *c, const std::string &key) {
+    for (auto &g : c->graphs)
+        if (g.key == key) return &g;
+    return nullptr;
+}
+void graph_clear(Ctx *c) {
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+int graph_begin(Ctx *c) {
+    if (c->capturing) return c->fail(KL_ERR_INVALID, "nested graph capture");
+    if (!c->cap_stream) KL_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    c->saved_stream = c->stream;
+    c->stream = c->cap_stream;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) {
+        c->stream = c->saved_stream;
+        return c->fail(KL_ERR_CUDA, "cudaStreamBeginCapture", e);
+    }
+    c->capturing = true;
+    return KL_OK;
+}
+int graph_end(Ctx *c, const std::string &key, double bytes, long long launches, Ctx::GraphEntry **out) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->stream = c->saved_stream;
+    c->capturing = false;
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        return c->fail(KL_ERR_CUDA, "cudaStreamEndCapture", e);
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return c->fail(KL_ERR_CUDA, "cudaGraphInstantiate", e);
+    }
+    if (c->graphs.size() >= 16) {      // small cache: the oldest entry goes
+        cudaGraphExecDestroy(c->graphs.front().exec);
+        c->graphs.erase(c->graphs.begin());
+    }
+    c->graphs.push_back(Ctx::GraphEntry{key, ex, bytes, launches});
+    *out = &c->graphs.back();
+    return KL_OK;
+}
+
 int ws_reserve(Ctx *c, size_t bytes) {
     if (bytes <= c->ws_bytes) return KL_OK;
+    graph_clear(c);     // cached graphs hold addresses inside the old arena
     if (c->ws) {
         cudaStreamSynchronize(c->stream);
         cudaFree(c->ws);
@@ -447,6 +495,7 @@ int kl_create(kl_handle_t *h, int device) {
     c->device = device;
     // experiment switches (same meaning as the options; options set later win)
     if (const char *e = getenv("KL_PDL")) c->opt_pdl = atoi(e) != 0;
+    if (const char *e = getenv("KL_USE_GRAPH")) c->opt_use_graph = atoi(e) != 0;
     if (const char *e = getenv("KL_STENCIL_TAIL")) c->opt_stencil_tail = atoi(e);
     if (const char *e = getenv("KL_STENCIL_STAGGER")) c->opt_stencil_stagger = atoi(e) != 0;
     if (const char *e = getenv("KL_STENCIL_ROWS")) c->opt_stencil_rows = atoi(e);
@@ -498,6 +547,8 @@ int kl_destroy(kl_handle_t h) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     prof_reset(c);
+    graph_clear(c);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -509,6 +560,7 @@ const char *kl_last_error(kl_handle_t h) { return h ? h->err.c_str() : "null han
 int kl_set_stream(kl_handle_t h, void *cuda_stream) {
     if (!h) return KL_ERR_INVALID;
     Ctx *c = h;
+    if (cuda_stream && !c->own_stream && c->stream == (cudaStream_t)cuda_stream) return KL_OK;
     cudaStreamSynchronize(c->stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (cuda_stream) {

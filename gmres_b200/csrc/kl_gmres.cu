@@ -376,7 +376,8 @@ bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc) {
 
 int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
                   const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated,
-                  long long tail0) {
+                  long long tail0, const double *tail_T, double *tail_tvec, int tail_ldt) {
+    const TsTail tt{tail_T, tail_tvec, tail_ldt};
     CUtensorMap tm;
     KL_TRY(tmap_encode_v(c, &tm, V, n, ldv, ncols_total, nc));
     const size_t smem = ts_tma_smem(nc);
@@ -393,10 +394,10 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     const int *fl = gated ? c->d_I : nullptr;
     if (update)
         k_ts_tma<true><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                              out, G, j, hm, fl, tail0);
+                                                              out, G, j, hm, fl, tail0, tt);
     else
         k_ts_tma<false><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                               out, G, j, hm, fl, tail0);
+                                                               out, G, j, hm, fl, tail0, tt);
     c->stats.kernel_launches++;
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, out, nc + (tail0 >= 0 ? 1 : 0)));
@@ -516,8 +517,13 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     const int max_restarts = c->opt_max_restarts;
     int status = KL_NOT_CONVERGED, n_out = 0, restart_out = max_restarts, cycles = 0;
     double bytes = 0.0;
-    for (int st = 1; st <= max_restarts; ++st) {
-        ++cycles;
+    double *const w_base = w, *const z_base = z;
+    // One restart cycle = a fixed sequence of launches (every pointer, column count and step index is known on
+    // the host; convergence is a device-side gate), so it can be captured once and replayed as a CUDA graph:
+    // at 300^2 (BASELINE config 1) a cycle is ~480 launches of 5-20 us kernels and launch overhead dominates.
+    auto enqueue_cycle = [&]() -> int {
+        w = w_base;
+        z = z_base;
         // g = 0 ; H = 0 (:312).  (V = 0 is not needed: every column is written before it is read.)
         KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
         KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
@@ -631,6 +637,44 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
         if (vec == 2) k_xpvy<2><<<upd_grid(n / 2), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
         else k_xpvy<1><<<upd_grid(n), kTsThreads, sizeof(double) * m, c->stream>>>(V, ldv, dx, n, G);
         c->stats.kernel_launches += 1;
+        return KL_OK;
+    };
+    const bool use_graph = c->opt_use_graph && !c->opt_profile && c->nranks == 1 && fused &&
+                           (P.pc.kind == KL_PC_NONE || P.pc.kind == KL_PC_CBPR2 || P.pc.kind == KL_PC_CHEB);
+    GraphKey gk;
+    if (use_graph) {
+        gk.add('G').add(nx).add(ny).add(m).add(mf).add(P.op.kind).add(P.op.eps_x).add(P.op.eps_y).add(P.pc.kind)
+            .add(P.pc.degree).add(P.params).add(c->opt_ortho).add(c->opt_reorth_eta_permille).add(c->opt_tma)
+            .add(c->opt_chain).add(c->opt_stencil_rows).add(c->opt_stencil_tail).add(c->opt_stencil_stagger)
+            .add(c->opt_pdl).add(c->ws).add(db).add(dx).add(V).add(G.H);
+    }
+    for (int st = 1; st <= max_restarts; ++st) {
+        ++cycles;
+        Ctx::GraphEntry *ge = use_graph ? graph_find(c, gk.s) : nullptr;
+        if (use_graph && !ge && st >= 2) {
+            // (the first cycle of a handle's first solve runs eagerly: it sets the function attributes and fills
+            // the tensor-map cache)
+            const double b0 = bytes;
+            const long long l0 = c->stats.kernel_launches;
+            KL_TRY(graph_begin(c));
+            const int rc = enqueue_cycle();
+            if (rc < 0) {
+                Ctx::GraphEntry *dummy = nullptr;
+                graph_end(c, std::string(), 0.0, 0, &dummy);
+                graph_clear(c);
+                return rc;
+            }
+            KL_TRY(graph_end(c, gk.s, bytes - b0, c->stats.kernel_launches - l0, &ge));
+            bytes = b0;
+            c->stats.kernel_launches = l0;
+        }
+        if (ge) {
+            KL_CUDA(c, cudaGraphLaunch(ge->exec, c->stream));
+            bytes += ge->bytes;
+            c->stats.kernel_launches += ge->launches;
+        } else {
+            KL_TRY(enqueue_cycle());
+        }
         KL_TRY(read_back(c));
         n_out = c->h_pinned_i[I_NOUT];
         bytes += (8.0 * n_out + 16.0) * n;
@@ -686,8 +730,15 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     c->stats.cycles = cycles;
     c->stats.solve_ms = ms;
     c->stats.total_ms = ms_tot;
-    // selective reorthogonalisation: the skipped second update passes moved no data
-    bytes -= (8.0 * c->h_pinned_i[I_NSKIPCOLS] + 16.0 * c->h_pinned_i[I_NSKIP]) * (double)n;
+    // selective reorthogonalisation: the skipped second update passes moved no data (neither in the per-iteration
+    // total nor in the per-kernel profile, where every launch was charged when it was enqueued)
+    const double skipped_bytes = (8.0 * c->h_pinned_i[I_NSKIPCOLS] + 16.0 * c->h_pinned_i[I_NSKIP]) * (double)n;
+    bytes -= skipped_bytes;
+    if (c->opt_profile && c->prof_launches[3] > 0) {
+        c->prof_bytes[3] -= skipped_bytes;
+        c->prof_launches[3] -= c->h_pinned_i[I_NSKIP];      // launches that returned at once are not counted
+        if (c->prof_launches[3] < 1) c->prof_launches[3] = 1;
+    }
     c->stats.algorithmic_bytes = bytes;
     c->stats.reorth_skipped = c->h_pinned_i[I_NSKIP];
     *n_out_p = n_out;

@@ -131,7 +131,7 @@ int launch_backsolve(Ctx *c, const GmresDev &G);
 bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc);
 int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
                   const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated,
-                  long long tail0 = -1);
+                  long long tail0 = -1, const double *tail_T = nullptr, double *tail_tvec = nullptr, int tail_ldt = 0);
 int gram_lower(Ctx *c, const double *V, size_t ldv, size_t n, int k, double *d_gram, std::vector<double> &out);
 
 }  // namespace kl

@@ -217,17 +217,6 @@ __global__ void __launch_bounds__(256) k_wy_pre(const GmresDev G, const HhWy W, 
         if (lane == 0) W.tvec[r] = t;
     }
 }
-// tvec(0..j) = T(0..j,0..j)^T * svec(0..j)
-__global__ void __launch_bounds__(256) k_wy_tT(const GmresDev G, const HhWy W, const int j) {
-    if (G.I[I_CONV_AT] >= 0) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int c = wid; c <= j; c += 8) {
-        double t = 0.0;
-        for (int r = lane; r <= c; r += 32) t = fma(W.T[(size_t)c * W.ldt + r], W.svec[r], t);
-        t = warp_sum(t);
-        if (lane == 0) W.tvec[c] = t;
-    }
-}
 // cycle end: svec = Ytop(0..k-1, 0..k-1)^T y ; tvec = T_k svec    (x += [y;0] - Y tvec)
 __global__ void k_wy_xs(const GmresDev G, const HhWy W, const int k) {
     extern __shared__ double sm[];
@@ -325,6 +314,8 @@ __global__ void k_hh_first_wy(const GmresDev G, const HhWy W, const double *w) {
     pv = __shfl_sync(0xffffffffu, pv, 0);
     nw = __shfl_sync(0xffffffffu, nw, 0);
     for (int r = lane; r <= G.m; r += 32) W.Ytop[r] = (r == 0 ? pv : w[r]) / nw;
+    // k_wy_pre of step 0, folded in: tvec(0) = T(0,0) * Ytop(0,0)
+    if (lane == 0) W.tvec[0] = 2.0 * (pv / nw);
 }
 
 // serial block of the reference in WY form: H(:,j), Householder pivot, new column of Ytop and of T
@@ -375,6 +366,18 @@ k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, c
         if (lane == 0) W.T[(size_t)(j + 1) * W.ldt + r] = -2.0 * t;
     }
     if (threadIdx.x == 0) W.T[(size_t)(j + 1) * W.ldt + j + 1] = 2.0;
+    // k_wy_pre of the NEXT step, folded in (one launch less on the critical path of every step):
+    //   tvec(0..j+1) = T(0..j+1, 0..j+1) * Ytop(row j+1, 0..j+1)
+    __syncthreads();
+    if (j + 1 < G.m) {
+        const int jn = j + 1;
+        for (int r = wid; r <= jn; r += 8) {
+            double t = 0.0;
+            for (int c = r + lane; c <= jn; c += 32) t = fma(W.T[(size_t)c * W.ldt + r], W.Ytop[(size_t)c * W.ldy + jn], t);
+            t = warp_sum(t);
+            if (lane == 0) W.tvec[r] = t;
+        }
+    }
     if (wid != 0) return;
     const int conv_before = G.I[I_CONV_AT];
     givens_update_warp(G, j, hj1, lane, sm, false);
@@ -504,8 +507,10 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
     const int max_stages = c->opt_max_restarts;
     int status = KL_NOT_CONVERGED, n_out = 0, stages_out = 0, cycles = 0;
     const size_t gsm = sizeof(double) * 3 * (m + 2);
-    for (int k = 1; k <= max_stages; ++k) {
-        ++cycles;
+    // The cycle up to the back substitution is a fixed launch sequence (the convergence test is a device-side gate):
+    // captured once and replayed as a CUDA graph (KL_OPT_USE_GRAPH).  At 1024^2 (BASELINE config 2) a step is
+    // 7 launches around ~250 us of work and the gaps between them were ~10 % of the step.
+    auto enqueue_cycle = [&]() -> int {
         // g = 0 ; H = 0 (:241).  P = 0 is implicit: every reflector is fully written before use.
         KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
         KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
@@ -535,8 +540,7 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
         for (int j = 0; j < m; ++j) {
             if (blocked) {
                 const int nc = j + 1;
-                // v_j = e_j - Y (T Ytop(j,:)^T)
-                k_wy_pre<<<1, 256, 0, c->stream>>>(G, W, j, 1);
+                // v_j = e_j - Y (T Ytop(j,:)^T) ; tvec = T Ytop(j,:)^T comes from the previous step's scalar kernel
                 KL_TRY(launch_apply_wy(c, Pm, ldv, nc, W.tvec, 1, j, nullptr, vj, 0, n, true));
                 if (prec) {
                     KL_TRY(op_apply(&P, vj, z, true));
@@ -545,11 +549,12 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
                     KL_TRY(op_apply(&P, vj, w, true));
                 }
                 // s = Y^T w ; t = T^T s ; w -= Y t fused with u = Y^T w and the tail norm
-                KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true));
-                k_wy_tT<<<1, 256, 0, c->stream>>>(G, W, j);
+                // (t = T^T s is computed by the last block of the projection kernel, kl_tallskinny_tma.cuh TsTail;
+                // tvec was consumed by launch_apply_wy above and is refilled for the next step by k_hh_step_wy)
+                KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true, -1, W.T, W.tvec, W.ldt));
                 KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
                 k_hh_step_wy<<<1, 256, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
-                c->stats.kernel_launches += 3;
+                c->stats.kernel_launches += 1;
                 PHhNewReflector f;
                 set_gate(f, c, true, j, 1);
                 f.w = w; f.p_out = Pm + (size_t)(j + 1) * ldv; f.S = c->d_S; f.piv = (long long)j + 1;
@@ -611,6 +616,42 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
             }
         }
         KL_TRY(launch_backsolve(c, G));                                    // :350-354
+        return KL_OK;
+    };
+    const bool use_graph = c->opt_use_graph && !c->opt_profile && P.builtin_op() && c->opt_fuse &&
+                           (P.pc.kind == KL_PC_NONE || P.pc.kind == KL_PC_CBPR2 || P.pc.kind == KL_PC_CHEB);
+    GraphKey gk;
+    if (use_graph) {
+        gk.add('H').add(nx).add(ny).add(m).add(prec_variant).add(P.op.kind).add(P.op.eps_x).add(P.op.eps_y)
+            .add(P.pc.kind).add(P.pc.degree).add(P.params).add(c->opt_hh_mode).add(c->opt_tma).add(c->opt_chain)
+            .add(c->opt_stencil_rows).add(c->opt_stencil_tail).add(c->opt_stencil_stagger).add(c->opt_verr)
+            .add(c->ws).add(db).add(dx).add(Pm).add(G.H);
+    }
+    for (int k = 1; k <= max_stages; ++k) {
+        ++cycles;
+        Ctx::GraphEntry *ge = use_graph ? graph_find(c, gk.s) : nullptr;
+        if (use_graph && !ge && k >= 2) {      // the first cycle of a handle's first solve runs eagerly
+            const double b0 = R.bytes;
+            const long long l0 = c->stats.kernel_launches;
+            KL_TRY(graph_begin(c));
+            const int rc = enqueue_cycle();
+            if (rc < 0) {
+                Ctx::GraphEntry *dummy = nullptr;
+                graph_end(c, std::string(), 0.0, 0, &dummy);
+                graph_clear(c);
+                return rc;
+            }
+            KL_TRY(graph_end(c, gk.s, R.bytes - b0, c->stats.kernel_launches - l0, &ge));
+            R.bytes = b0;
+            c->stats.kernel_launches = l0;
+        }
+        if (ge) {
+            KL_CUDA(c, cudaGraphLaunch(ge->exec, c->stream));
+            R.bytes += ge->bytes;
+            c->stats.kernel_launches += ge->launches;
+        } else {
+            KL_TRY(enqueue_cycle());
+        }
         KL_TRY(read_back(c));
         n_out = c->h_pinned_i[I_NOUT];
         // w = [y;0] ; w = P_0 ... P_{n_out-1} w ; x += w  (:356-378)

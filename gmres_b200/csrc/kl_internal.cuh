@@ -164,6 +164,13 @@ struct kl_context_s {
     // halo buffers (multi GPU): up to 4 vectors x 2 directions
     double *d_halo = nullptr;
     size_t halo_doubles = 0;
+    // CUDA-graph replay of iteration batches / restart cycles (KL_OPT_USE_GRAPH): executable graphs cached by a
+    // key that holds everything baked into the captured launches (problem, options, buffer addresses)
+    struct GraphEntry { std::string key; cudaGraphExec_t exec; double bytes; long long launches; };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;     // capture happens here (the user stream may be the legacy stream)
+    cudaStream_t saved_stream = nullptr;
+    bool capturing = false;
     // stats
     kl_stats_t stats{};
     std::vector<double> history;
@@ -213,6 +220,17 @@ struct ProfScope {
     Ctx *c;
     ProfScope(Ctx *c_, int cls, const char *name, double bytes) : c(c_) { if (c->opt_profile) prof_begin(c, cls, name, bytes); }
     ~ProfScope() { if (c->opt_profile) prof_end(c); }
+};
+
+// CUDA-graph helpers (kl_core.cu).  graph_find: cached executable graph or nullptr.  graph_begin redirects
+// c->stream to the capture stream; graph_end instantiates, caches under `key` and restores c->stream.
+Ctx::GraphEntry *graph_find(Ctx *c, const std::string &key);
+int graph_begin(Ctx *c);
+int graph_end(Ctx *c, const std::string &key, double bytes, long long launches, Ctx::GraphEntry **out);
+void graph_clear(Ctx *c);
+struct GraphKey {     // append-only byte string
+    std::string s;
+    template <class T> GraphKey &add(const T &v) { s.append(reinterpret_cast<const char *>(&v), sizeof(T)); return *this; }
 };
 
 // workspace arena

@@ -22,12 +22,31 @@ constexpr int kTsNst = 4;    // ring depth
 // eight warps split into RM row groups x 8/RM column slices
 inline int ts_rm(int nc) { return nc <= 12 ? 8 : (nc <= 24 ? 4 : (nc <= 48 ? 2 : 1)); }
 
+// Optional epilogue of the projection kernel's last block (compact-WY Householder GMRES, kl_hh.cu):
+//   tvec(0..nc-1) = T(0..nc-1, 0..nc-1)^T out(0..nc-1)   -- the O(j^2) triangular product that sits between the two
+// tall-skinny passes of a step; run by the eight warps of the last block instead of a kernel of its own.
+struct TsTail {
+    const double *T;    // nullptr: no epilogue
+    double *tvec;
+    int ldt;
+};
+static __device__ __noinline__ void ts_tail_tT(const TsTail tt, const double *s, const int nc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = wid; c < nc; c += kTsWarps) {
+        double t = 0.0;
+        for (int r = lane; r <= c; r += 32) t = fma(tt.T[(size_t)c * tt.ldt + r], s[r], t);
+        t = warp_sum(t);
+        if (lane == 0) tt.tvec[c] = t;
+    }
+}
+
 template <bool UPDATE>
 __global__ void __launch_bounds__(kTsThreads, 2)
 k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, const int nc, const int RM,
          const double *__restrict__ h_in, double *__restrict__ partials, unsigned int *counter,
          double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
-         const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */) {
+         const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */,
+         const TsTail tt) {
     if (flags && flags[I_CONV_AT] >= 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -165,6 +184,10 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
         }
     }
     if (threadIdx.x == 0) *counter = 0u;
+    if (!UPDATE && tt.T) {
+        __syncthreads();          // out[] was written by this block's warps
+        ts_tail_tT(tt, out, nc);
+    }
 }
 
 inline size_t ts_tma_smem(int nc) {

@@ -96,7 +96,9 @@ int kl_create(kl_handle_t *h, int device);
 int kl_destroy(kl_handle_t h);
 const char *kl_last_error(kl_handle_t h);
 int kl_version(void);
-/* use an existing CUDA stream (e.g. torch's current stream); NULL = own stream */
+/* use an existing CUDA stream (e.g. torch's current stream; pass cudaStreamLegacy = (void*)1 for the legacy default
+ * stream); NULL = the handle's own non-blocking stream.  In device-pointer mode the caller's vectors must be
+ * ordered against the handle's stream: either share the stream that produces / consumes them, or synchronise. */
 int kl_set_stream(kl_handle_t h, void *cuda_stream);
 int kl_synchronize(kl_handle_t h);
 

@@ -34,10 +34,30 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def build_native() -> str:
+    """A copy built with -march=native (the reference's own flag, CMakeLists.txt:5) on THIS machine, for timing
+    the CPU baseline on the box it runs on.  The portable x86-64-v3 build stays the checker.  Returns the path
+    (or the portable library's path if the compiler is missing)."""
+    global _SO, _lib
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, "libkrylov_oracle.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O3", "-fopenmp", "-march=native", "-funroll-loops", "-ffp-contract=off", "-fPIC", "-std=gnu11",
+             "-shared", "-o", so, os.path.join(_HERE, "krylov_oracle.c"), os.path.join(_HERE, "krylov_extras.c"), "-lm"],
+            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return build()
+    _SO, _lib = so, None
+    return so
+
+
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if not _SO.endswith(os.path.join("_native", "libkrylov_oracle.so")):
+            build()
         L = C.CDLL(_SO)
         for name in ("ko_get_stvec", "ko_get_stv_poisson", "ko_get_aniso"):
             getattr(L, name).restype = STENCIL_FN

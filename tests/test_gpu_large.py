@@ -5,6 +5,8 @@ size-independent properties of the manufactured problem (b in {0,1,2}, ||b|| = s
 import numpy as np
 import pytest
 
+from parity import hist_norm, hist_rel
+
 pytestmark = pytest.mark.gpu
 P = (8.2, 0.2)
 
@@ -87,7 +89,7 @@ def test_pbicgstab_aniso_8192_vs_torch_fp64(env):
 
 def test_gmres_mgsr_4096_cycle_vs_torch_fp64(env):
     kl, h, torch = env
-    n, m = 4096, 24
+    n, m = 4096, 95          # BASELINE config 3's restart length: one full cycle
     b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
     h.set_option(2, 1)    # one restart cycle
     try:
@@ -119,3 +121,63 @@ def test_gmres_mgsr_4096_cycle_vs_torch_fp64(env):
     print("gmres4096 cycle history rel diff", rel.max())
     assert g.n_out == m and rel.max() < 1e-10
     assert np.all(np.diff(g.history[:m]) <= 0)     # GMRES residual estimate is monotone within a cycle
+
+
+def test_gmres_hh_1024_cycle_vs_oracle(env, ko):
+    """BASELINE config 2 at its own size: Householder GMRES, 1024^2, m = 95, one full cycle (gmres_hh_omp never
+    leaves a cycle early, gmres_hh.f90:340-344) against the oracle, in both reflector modes.  The bar on the
+    point-wise history is max(1e-10, 2 x the reference's own 1-thread vs 8-thread difference on this very case),
+    orthogonality "at the reference's level" = within 10x of the oracle's ||I - V^T V||_F and < 1e-27 in
+    calculate_verr's metric (README.md:10)."""
+    kl, h, torch = env
+    ns, m = 1024, 95
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    ko.set_threads(1)
+    o1 = ko.gmres_hh(ko.stvec_fn(), b, m, 0.0, None, max_stages=1, want_orth=True)
+    ko.set_threads(8)
+    o8 = ko.gmres_hh(ko.stvec_fn(), b, m, 0.0, None, max_stages=1, skip_verr=True)
+    ko.set_threads(1)
+    floor = hist_rel(o8.history, o1.history)
+    bar = max(1e-10, 2.0 * floor)
+    h.set_option(2, 1)
+    h.set_option(3, 1)
+    try:
+        for mode in (1, 0):
+            h.set_option(6, mode)
+            g = h.gmres_hh_omp(kl.stvec, b, m, 0.0)
+            d = hist_rel(g.history, o1.history)
+            print(f"hh1024 mode {mode}: history rel {d:.2e} (reference's own floor {floor:.2e}), x diff "
+                  f"{np.abs(g.x - o1.x).max():.2e}, v_err max {g.v_err.max():.2e} (oracle {o1.v_err.max():.2e}), "
+                  f"frob {g.stats['orth_frobenius']:.2e} (oracle {o1.orth_frob:.2e})")
+            assert (g.n_out, g.restart_out) == (o1.n_out, o1.restart_out) == (m, 1)
+            assert d < bar and hist_norm(g.history, o1.history) < 1e-10
+            assert np.abs(g.x - o1.x).max() < 1e-9 * np.abs(o1.x).max()
+            assert g.v_err.max() < 1e-27 and g.stats["orth_frobenius"] < max(10 * o1.orth_frob, 1e-13)
+    finally:
+        h.set_option(6, 1)
+        h.set_option(3, 0)
+        h.set_option(2, 1000)
+
+
+@pytest.mark.parametrize("ortho", [0, 1])
+def test_gmres_mgsr_300_at_the_drivers_tolerance(env, ko, ortho):
+    """BASELINE config 1 with the reference driver's own tolerance, tol = 1.d-15 (tests/test_poisson_mf.f90:64):
+    the stopping test sits at the rounding floor of the residual estimate, so the north star's +-1 iteration."""
+    kl, h, torch = env
+    ns, m = 300, 95
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    ko.set_threads(8)
+    o = ko.gmres_mgsr_omp(ko.stvec_fn(), b, m, 1e-15, ko.cbpr2_fn(), P, skip_verr=True)
+    ko.set_threads(1)
+    h.set_ortho(ortho)
+    try:
+        g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-15, kl.cbpr2, P)
+    finally:
+        h.set_ortho(1)
+    gi, oi = (g.restart_out - 1) * m + g.n_out, (o.restart_out - 1) * m + o.n_out
+    k = min(g.history.size, o.history.size)
+    print(f"gmres 300^2 tol 1e-15 ortho {ortho}: its gpu {gi} oracle {oi}; first cycle rel {hist_rel(g.history[:m], o.history[:m]):.2e}; "
+          f"normalised {hist_norm(g.history[:k], o.history[:k]):.2e}; L_inf error {np.abs(g.x - 1).max():.2e} (oracle {np.abs(o.x - 1).max():.2e})")
+    assert g.status == 0 and abs(gi - oi) <= 1
+    assert hist_rel(g.history[:m], o.history[:m]) < 1e-10 and hist_norm(g.history[:k], o.history[:k]) < 1e-10
+    assert np.abs(g.x - o.x).max() < 1e-9 and np.abs(g.x - 1).max() < 1e-10

@@ -11,6 +11,8 @@ import os
 import numpy as np
 import pytest
 
+from parity import hist_bar, hist_norm, hist_rel
+
 pytestmark = pytest.mark.gpu
 
 P = (8.2, 0.2)  # tests/test_poisson_mf.f90:38
@@ -96,7 +98,9 @@ def test_cg_parity(kl, h, ko, ns):
     rel = np.abs(g.history[:k] / o.history[:k] - 1)
     print(f"cg {ns}: iters gpu {g.iter} oracle {o.iter}; history rel diff head {rel[:50].max():.2e} all {rel.max():.2e}")
     assert rel[:50].max() < 1e-10
-    assert rel.max() < 1e-6
+    # whole history: max(1e-10, 2 x the reference's own 1-thread vs T-thread drift), tests/parity.py
+    assert rel.max() < hist_bar(f"cg_omp_{ns}"), (rel.max(), hist_bar(f"cg_omp_{ns}"))
+    assert hist_norm(g.history, o.history, float(np.linalg.norm(b))) < 1e-10
     assert np.abs(g.x - o.x).max() / np.abs(o.x).max() < 1e-9
     assert np.abs(g.x - 1).max() < 1e-9
     g2 = h.cg(kl.stvec, b, 1e-9, 10000)
@@ -112,7 +116,9 @@ def test_pcg_parity(kl, h, ko, ns):
     k = min(g.history.size, o.history.size)
     rel = np.abs(g.history[:k] / o.history[:k] - 1)
     print(f"pcg {ns}: iters gpu {g.iter} oracle {o.iter}; history rel diff head {rel[:50].max():.2e} all {rel.max():.2e}")
-    assert rel[:50].max() < 1e-10 and rel.max() < 1e-6
+    assert rel[:50].max() < 1e-10
+    assert rel.max() < hist_bar(f"pcg_omp_{ns}"), (rel.max(), hist_bar(f"pcg_omp_{ns}"))
+    assert hist_norm(g.history, o.history, float(np.linalg.norm(b))) < 1e-10
     assert np.abs(g.x - o.x).max() / np.abs(o.x).max() < 1e-9
 
 
@@ -156,9 +162,16 @@ def test_gmres_mgsr_parity(kl, h, ko, ns, m, tol, ortho):
           f"x rel {np.abs(g.x - o.x).max():.2e}; verr gpu {g.v_err[g.n_out]:.2e} oracle {o.v_err[o.n_out]:.2e}")
     assert g.status == 0 and abs(gi - oi) <= 1
     if tol >= 1e-8:
-        assert rel.max() < 1e-8          # see DESIGN.md: MGS vs CGS2 differ by ~3e-10 on the CPU too
+        # first restart cycle: 1e-10 point-wise (ortho = 0 restates the reference's MGS x2 order; CGS2 computes the
+        # same projections in another order).  Whole history: max(1e-10, 2 x the reference's own thread-count
+        # drift) point-wise and 1e-10 relative to beta0.
+        k1 = min(m, 50)
+        assert rel[:k1].max() < 1e-10, rel[:k1].max()
+        bar = hist_bar(f"gmres_mgsr_omp_{ns}_{m}")
+        assert rel.max() < bar, (rel.max(), bar)
+        assert hist_norm(g.history, o.history) < 1e-10
         assert np.abs(g.x - o.x).max() < 1e-9
-        assert np.abs(g.final_err[: g.n_out] / o.final_err[: o.n_out] - 1).max() < 1e-8 or gi != oi
+        assert np.abs(g.final_err[: g.n_out] / o.final_err[: o.n_out] - 1).max() < bar or gi != oi
     assert g.v_err[g.n_out] < 1e-12 and g.stats["orth_frobenius"] < 1e-12
     assert np.abs(g.x - 1).max() < max(1e4 * tol, 1e-11)
 
@@ -243,7 +256,9 @@ def test_gmres_hh_prec_parity(kl, h, ko, ns, m):
     print(f"hh_prec ns={ns} m={m}: its gpu {gi} oracle {oi}; hist rel {rel.max():.2e}; x diff {np.abs(g.x - o.x).max():.2e}; "
           f"v_err max gpu {g.v_err.max():.2e} oracle {o.v_err.max():.2e}; frob gpu {g.stats['orth_frobenius']:.2e} oracle {o.orth_frob:.2e}")
     assert g.status == 0 and abs(gi - oi) <= 1
-    assert rel.max() < 1e-8 and np.abs(g.x - o.x).max() < 1e-9
+    bar = hist_bar(f"gmres_hh_prec_omp_{ns}_{m}")
+    assert rel[: min(m, 50)].max() < 1e-10 and rel.max() < bar, (rel.max(), bar)
+    assert hist_norm(g.history, o.history) < 1e-10 and np.abs(g.x - o.x).max() < 1e-9
     # orthogonality at the reference's level (README.md:10: ~1e-30 in calculate_verr's metric)
     assert g.v_err.max() < 1e-27 and g.stats["orth_frobenius"] < 1e-11
 
@@ -307,6 +322,52 @@ def test_user_operator_callback(kl, h, ko):
     h2.close()
 
 
+def test_user_preconditioner_callback(kl, h, ko):
+    """procedure(precond) passed by the caller (interfaces.f90:19-28): a Python callback that receives the solver's
+    operator A_x, r, z, the solver-owned scratch aux and params -- the reference's dummy-argument list -- and
+    enqueues cbpr2 (chebyshev.f90:8-38) on the given stream through a second handle.  Same iteration counts and
+    solutions as the built-in descriptor, in PCG, GMRES-MGSR, Householder GMRES and BiCGSTAB."""
+    import ctypes as C
+    ns = 64
+    h2 = kl.Handle(0)
+    L = kl.load_library()
+    calls = []
+
+    def my_pc(a_x, d_r, d_z, d_aux, params, nx, nyl, stream):
+        assert d_aux and d_aux not in (d_r, d_z) and list(params) == list(P)
+        calls.append(stream)
+        pc, _ = kl.cbpr2._c()
+        prm = (C.c_double * len(params))(*params)
+        L.kl_set_pointer_mode(h2._h, 1)
+        L.kl_set_stream(h2._h, C.c_void_p(stream))
+        rc = L.kl_apply_precond(h2._h, C.byref(pc), C.cast(a_x, C.POINTER(kl.api.kl_operator_t)), C.c_void_p(d_r),
+                                C.c_void_p(d_z), prm, len(params), nx, nyl)
+        assert rc == 0
+
+    user = kl.Precond(100, fn=my_pc)
+    b = ko.manufactured_rhs(ko.stvec_fn(), ns)
+    g, r = h.pcg_omp(kl.stvec, b, 1e-9, 10000, user, P), h.pcg_omp(kl.stvec, b, 1e-9, 10000, kl.cbpr2, P)
+    assert g.status == 0 and g.iter == r.iter and np.allclose(g.x, r.x, rtol=0, atol=1e-12)
+    n_pcg = len(calls)
+    assert n_pcg == g.iter + 1 or n_pcg >= g.iter          # z0 = M^-1 r0 plus one application per iteration
+    g, r = h.gmres_mgsr_omp(kl.stvec, b, 30, 1e-8, user, P), h.gmres_mgsr_omp(kl.stvec, b, 30, 1e-8, kl.cbpr2, P)
+    assert g.status == 0 and _its(g, 30) == _its(r, 30) and np.allclose(g.x, r.x, rtol=0, atol=1e-12)
+    g, r = h.gmres_hh_prec_omp(kl.stvec, b, 30, 1e-8, user, P), h.gmres_hh_prec_omp(kl.stvec, b, 30, 1e-8, kl.cbpr2, P)
+    assert g.status == 0 and _its(g, 30) == _its(r, 30) and np.allclose(g.x, r.x, rtol=0, atol=1e-11)
+    g, o = h.pbicgstab_omp(kl.stvec, b, 1e-9, 10000, user, P), ko.pbicgstab_omp(ko.stvec_fn(), b, 1e-9, 10000, ko.cbpr2_fn(), P)
+    assert g.status == 0 and abs(g.iter - o.iter) <= 3 and np.abs(g.x - 1).max() < 1e-7
+    # and on a user OPERATOR (both plug-ins supplied by the caller, as in the reference's drivers)
+    def my_op(dx, dy, nx, nyl, stream):
+        o_, _ = kl.stvec._c()
+        L.kl_set_pointer_mode(h2._h, 1)
+        L.kl_set_stream(h2._h, C.c_void_p(stream))
+        assert L.kl_apply_operator(h2._h, C.byref(o_), C.c_void_p(dx), C.c_void_p(dy), nx, nyl) == 0
+    g = h.pcg_omp(kl.Operator(100, fn=my_op), b, 1e-9, 10000, user, P)
+    r = h.pcg_omp(kl.stvec, b, 1e-9, 10000, kl.cbpr2, P)
+    assert g.status == 0 and g.iter == r.iter and np.allclose(g.x, r.x, rtol=0, atol=1e-12)
+    h2.close()
+
+
 def test_fast_division_is_ieee_exact(kl, h, ko):
     """The kernels divide by a kernel-constant with a hoisted reciprocal + two Markstein
     corrections (kl_internal.cuh FastDiv); it must round exactly like the reference's r(i)/d."""
@@ -342,7 +403,9 @@ def test_gmres_hh_blocked_compact_wy(kl, h, ko, ns, m):
     print(f"hh_blocked ns={ns} m={m}: its gpu {gi} oracle {oi}; hist rel {rel.max():.2e}; x diff {np.abs(g.x - o.x).max():.2e}; "
           f"v_err max {g.v_err.max():.2e}; frob {g.stats['orth_frobenius']:.2e}")
     assert g.status == 0 and abs(gi - oi) <= 1
-    assert rel.max() < 1e-8 and np.abs(g.x - o.x).max() < 1e-9
+    bar = hist_bar(f"gmres_hh_prec_omp_{ns}_{m}")
+    assert rel[: min(m, 50)].max() < 1e-10 and rel.max() < bar, (rel.max(), bar)
+    assert hist_norm(g.history, o.history) < 1e-10 and np.abs(g.x - o.x).max() < 1e-9
     assert g.v_err.max() < 1e-27 and g.stats["orth_frobenius"] < 1e-11
     if g0 is not None:
         assert g0.status == 0 and np.abs(g0.x - 1).max() < 1e-4
@@ -372,7 +435,8 @@ def test_gmres_selective_reorthogonalisation(kl, h, ko, ns, m):
         assert np.abs(r.x - o.x).max() < 1e-7
     assert g.stats["orth_frobenius"] < 1e-11
     k = min(g.history.size, o.history.size)
-    assert np.abs(g.history[:k] / o.history[:k] - 1).max() < 1e-6
+    assert np.abs(g.history[:k] / o.history[:k] - 1).max() < hist_bar(f"gmres_mgsr_omp_{ns}_{m}")
+    assert hist_norm(g.history, o.history) < 1e-10 and hist_norm(g1.history, o.history) < 1e-10
     assert g1.stats["reorth_skipped"] > 0.5 * g1.stats["iterations"] and g1.stats["orth_frobenius"] < 1e-4
 
 

@@ -25,6 +25,8 @@ import os
 import numpy as np
 import pytest
 
+from parity import hist_norm, hist_rel as rel_hist, x_diff
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P_REF = (8.2, 0.2)
 
@@ -33,30 +35,6 @@ P_REF = (8.2, 0.2)
 def ref():
     with open(os.path.join(ROOT, "tests", "golden", "reference_f90.json")) as f:
         return json.load(f)["cases"]
-
-
-def rel_hist(a, b, floor=1e-12):
-    a, b = np.asarray(a), np.asarray(b)
-    k = min(a.size, b.size)
-    a, b = a[:k], b[:k]
-    m = np.abs(b) > floor
-    return float(np.max(np.abs(a[m] / b[m] - 1.0))) if m.any() else 0.0
-
-
-def hist_norm(a, b, r0=1.0):
-    a, b = np.asarray(a), np.asarray(b)
-    k = min(a.size, b.size)
-    return float(np.max(np.abs(a[:k] - b[:k]))) / r0 if k else 0.0
-
-
-def x_diff(x, c):
-    """max difference between a computed solution and the stored one (full vector, or head + sums for big grids)"""
-    if "x" in c:
-        return float(np.max(np.abs(x - np.array(c["x"]))))
-    h = np.array(c["x_head"])
-    d = float(np.max(np.abs(x[: h.size] - h)))
-    d = max(d, abs(float(np.sum(x)) - c["x_sum"]) / x.size)
-    return max(d, abs(float(np.max(np.abs(x - 1.0))) - c["x_err_inf"]))
 
 
 def cases(ref, prefix):
@@ -210,4 +188,6 @@ def test_oracle_noise_floor(ko):
     d_cg, d_gm = rel_hist(cT.history, c1.history), rel_hist(gT.history, g1.history)
     # drift exists (the reference is not bit-reproducible) and is of the size the committed record says
     assert 0.0 < d_cg < 100 * committed["cg_omp_128"]["history_rel"] + 1e-9
-    assert 0.0 < d_gm < 100 * committed["gmres_mgsr_omp_128"]["history_rel"] + 1e-9
+    assert 0.0 < d_gm < 100 * committed["gmres_mgsr_omp_128_95"]["history_rel"] + 1e-9
+    # and the reference's BiCGSTAB does not even keep its iteration count between thread counts
+    assert len(set(committed["pbicgstab_omp_300"]["iterations"])) > 1
