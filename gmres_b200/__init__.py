@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     stvec,
     stv_poisson,
     aniso,
+    aniso_var,
     cbpr2,
     cheb,
     no_precond,

@@ -28,7 +28,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBNAME = "libkrylov_b200.so"
 
 KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN = 0, 1, 2
-KL_OP_POISSON5, KL_OP_POISSON5_BRANCHY, KL_OP_ANISO5, KL_OP_USER = 0, 1, 2, 100
+KL_OP_POISSON5, KL_OP_POISSON5_BRANCHY, KL_OP_ANISO5, KL_OP_ANISO5_VAR, KL_OP_USER = 0, 1, 2, 4, 100
 KL_PC_NONE, KL_PC_CBPR2, KL_PC_CHEB, KL_PC_USER = 0, 1, 2, 100
 KL_POINTER_HOST, KL_POINTER_DEVICE = 0, 1
 (KL_OPT_ORTHO, KL_OPT_MAX_RESTARTS, KL_OPT_VERR, KL_OPT_CHECK_EVERY, KL_OPT_USE_GRAPH,
@@ -49,6 +49,10 @@ PRECOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 class kl_operator_t(C.Structure):
     _fields_ = [("kind", C.c_int), ("eps_x", C.c_double), ("eps_y", C.c_double),
                 ("fn", APPLY_FN), ("user", C.c_void_p)]
+
+
+class kl_aniso_var_t(C.Structure):
+    _fields_ = [("kx", C.c_void_p), ("ky", C.c_void_p)]
 
 
 class kl_precond_t(C.Structure):
@@ -144,11 +148,16 @@ class Operator:
     eps_x: float = 1.0
     eps_y: float = 1.0
     fn: Optional[object] = None  # python callable(d_x:int, d_y:int, nx, ny_local, stream:int) for KL_OP_USER
+    coef: Optional[tuple] = None  # (kx, ky) CUDA float64 tensors for KL_OP_ANISO5_VAR
 
     def _c(self):
         o = kl_operator_t()
         o.kind, o.eps_x, o.eps_y = self.kind, self.eps_x, self.eps_y
         keep = None
+        if self.kind == KL_OP_ANISO5_VAR:
+            kx, ky = self.coef
+            keep = kl_aniso_var_t(C.c_void_p(kx.data_ptr()), C.c_void_p(ky.data_ptr()))
+            o.user = C.cast(C.pointer(keep), C.c_void_p)
         if self.kind == KL_OP_USER:
             f = self.fn
 
@@ -210,6 +219,19 @@ no_precond = Precond(KL_PC_NONE)
 
 def aniso(eps_x: float, eps_y: float) -> Operator:
     return Operator(KL_OP_ANISO5, float(eps_x), float(eps_y))
+
+
+def aniso_var(kx, ky) -> Operator:
+    """Variable-coefficient anisotropic diffusion (KL_OP_ANISO5_VAR): cell coefficient grids kx(i,j), ky(i,j) as numpy
+    arrays or CUDA tensors of nx*ny values (idx = i + j*nx); they are kept on the device by the returned descriptor."""
+    import torch
+
+    def dev(a):
+        if _is_torch_cuda(a):
+            return a.contiguous().reshape(-1)
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).cuda()
+
+    return Operator(KL_OP_ANISO5_VAR, coef=(dev(kx), dev(ky)))
 
 
 def cheb(degree: int) -> Precond:

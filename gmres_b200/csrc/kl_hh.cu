@@ -140,7 +140,7 @@ struct PHhNewReflector : PwBase<0> {
 };
 
 // serial block of the reference by ONE WARP (gmres_hh.f90:305-345 / :486-526)
-__global__ void k_hh_step(const GmresDev G, const double *w, const int j, const int prec_variant) {
+__global__ void k_hh_step(const GmresDev G, const double *w, const int j, const int prec_variant, const long long n) {
     extern __shared__ double sm[];
     if (G.I[I_CONV_AT] >= 0) return;
     const int lane = threadIdx.x;
@@ -153,13 +153,19 @@ __global__ void k_hh_step(const GmresDev G, const double *w, const int j, const 
     }
     double hj1 = 0.0;
     if (lane == 0) {
-        const double S2 = G.S[S_RED];
-        const double piv = w[j + 1];
-        const double tmp = sqrt(fma(piv, piv, S2));          // :308 norm2(w(j+1:n))
-        hj1 = (piv > 0.0) ? -tmp : tmp;                      // :309-313
-        const double pv = piv - hj1;                         // :316
-        G.S[S_TMP1] = pv;
-        G.S[S_NORM] = sqrt(fma(pv, pv, S2));                 // :317 norm2(w)
+        if ((long long)j + 1 < n) {                              // :307 if (j < n)
+            const double S2 = G.S[S_RED];
+            const double piv = w[j + 1];
+            const double tmp = sqrt(fma(piv, piv, S2));          // :308 norm2(w(j+1:n))
+            hj1 = (piv > 0.0) ? -tmp : tmp;                      // :309-313
+            const double pv = piv - hj1;                         // :316
+            G.S[S_TMP1] = pv;
+            G.S[S_NORM] = sqrt(fma(pv, pv, S2));                 // :317 norm2(w)
+        } else {                                                 // j = n (m = n): no reflector left, H(j+1,j) = 0 (:66-67)
+            hj1 = 0.0;
+            G.S[S_TMP1] = 0.0;
+            G.S[S_NORM] = 1.0;
+        }
     }
     hj1 = __shfl_sync(0xffffffffu, hj1, 0);
     __syncwarp();
@@ -441,7 +447,8 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
     KL_TRY(prob_init(&P, c, A, prec_variant == 1 ? M : nullptr, params, nparams, nx, ny));
     const bool prec = P.pc.kind != KL_PC_NONE;
     const size_t n = P.n;
-    if ((size_t)m + 1 >= n) return c->fail(KL_ERR_INVALID, "m must be smaller than the number of unknowns");
+    // j runs to m and the reference indexes v_j(j), so m <= n; m = n takes the `j < n` else-branch (gmres_hh.f90:53,66)
+    if ((size_t)m > n) return c->fail(KL_ERR_INVALID, "m must not exceed the number of unknowns");
     const size_t ldv = (n + 31) & ~size_t(31);
     const int ldh = m + 1;
     c->stats = kl_stats_t{};
@@ -605,7 +612,7 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
                 KL_TRY(launch_pointwise(c, f, n, NoPost{}));
                 R.bytes += 24.0 * n;
             }
-            k_hh_step<<<1, 32, gsm, c->stream>>>(G, w, j, prec_variant);   // :305-345
+            k_hh_step<<<1, 32, gsm, c->stream>>>(G, w, j, prec_variant, (long long)n);   // :305-345
             c->stats.kernel_launches++;
             {
                 PHhNewReflector f;                                          // :315-318

@@ -18,9 +18,15 @@ int prob_init(Prob *P, Ctx *c, const kl_operator_t *op, const kl_precond_t *pc, 
     P->op = *op;
     if (pc) P->pc = *pc;
     else P->pc = kl_precond_t{KL_PC_NONE, 0, nullptr, nullptr};
-    if (P->op.kind != KL_OP_POISSON5 && P->op.kind != KL_OP_POISSON5_BRANCHY &&
-        P->op.kind != KL_OP_ANISO5 && P->op.kind != KL_OP_USER && P->op.kind != KL_OP_DENSE)
+    if (P->op.kind != KL_OP_POISSON5 && P->op.kind != KL_OP_POISSON5_BRANCHY && P->op.kind != KL_OP_ANISO5 &&
+        P->op.kind != KL_OP_USER && P->op.kind != KL_OP_DENSE && P->op.kind != KL_OP_ANISO5_VAR)
         return c->fail(KL_ERR_INVALID, "unknown operator kind");
+    if (P->op.kind == KL_OP_ANISO5_VAR) {
+        const kl_aniso_var_t *cf = (const kl_aniso_var_t *)P->op.user;
+        if (!cf || !cf->kx || !cf->ky) return c->fail(KL_ERR_INVALID, "KL_OP_ANISO5_VAR without coefficient arrays");
+        if (c->nranks > 1) return c->fail(KL_ERR_UNSUPPORTED, "variable-coefficient operators are single-GPU only");
+        if (ny > 65535) return c->fail(KL_ERR_UNSUPPORTED, "KL_OP_ANISO5_VAR: ny <= 65535");
+    }
     if (P->op.kind == KL_OP_USER && !P->op.fn) return c->fail(KL_ERR_INVALID, "KL_OP_USER without callback");
     if (P->op.kind == KL_OP_USER && c->nranks > 1)
         return c->fail(KL_ERR_UNSUPPORTED, "user operators are single-GPU only");
@@ -78,8 +84,36 @@ int halo_exchange_lines(Prob *P, const double *const *vecs, int nvec, int nlines
     return comm_halo_exchange(c, slo, shi, H->lo, H->hi, nvec, nlines * P->nx);
 }
 
+// Variable-coefficient anisotropic diffusion, y = A(kx, ky) x (definition and evaluation order: oracle/krylov_extras.c
+// ko_aniso_var).  One thread per pair of grid points, neighbours through L1/L2; the operator takes the generic solver
+// path (one kernel per reference loop), like a user operator.  32n B (x, kx, ky in, y out).
+__global__ void __launch_bounds__(256)
+k_aniso_var(const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ kx,
+            const double *__restrict__ ky, const int nx, const int ny, const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    const int i = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+    if (i >= nx) return;
+    const size_t idx = (size_t)i + (size_t)j * nx;
+    const double kxc = __ldg(kx + idx), kyc = __ldg(ky + idx), xc = __ldg(x + idx);
+    const bool hl = i > 0, hr = i < nx - 1, hu = j > 0, hd = j < ny - 1;
+    const double wl = hl ? 0.5 * (kxc + __ldg(kx + idx - 1)) : kxc, wr = hr ? 0.5 * (kxc + __ldg(kx + idx + 1)) : kxc;
+    const double wu = hu ? 0.5 * (kyc + __ldg(ky + idx - nx)) : kyc, wd = hd ? 0.5 * (kyc + __ldg(ky + idx + nx)) : kyc;
+    const double xl = hl ? __ldg(x + idx - 1) : 0.0, xr = hr ? __ldg(x + idx + 1) : 0.0;
+    const double xd = hd ? __ldg(x + idx + nx) : 0.0, xu = hu ? __ldg(x + idx - nx) : 0.0;
+    const double diag = ((wl + wr) + wd) + wu;
+    const double s = fma(wl, xl, wr * xr), t = fma(wd, xd, wu * xu);
+    y[idx] = fma(diag, xc, -(s + t));
+}
+
 int op_apply(Prob *P, const double *x, double *y, bool gated) {
     Ctx *c = P->c;
+    if (P->op.kind == KL_OP_ANISO5_VAR) {
+        const kl_aniso_var_t *cf = (const kl_aniso_var_t *)P->op.user;
+        dim3 grid((unsigned)((P->nx + 255) / 256), (unsigned)P->nyl);
+        k_aniso_var<<<grid, 256, 0, c->stream>>>(x, y, cf->kx, cf->ky, P->nx, P->nyl, gated ? c->d_I : nullptr);
+        c->stats.kernel_launches++;
+        return KL_OK;
+    }
     if (P->op.kind == KL_OP_DENSE) return launch_gemv(c, (const double *)P->op.user, P->nx, x, y, gated);
     if (!P->builtin_op()) {
         // user callbacks cannot be gated on the device flag; they run unconditionally

@@ -64,8 +64,15 @@ enum {
     KL_OP_ANISO5 = 2,            /* constant-coefficient anisotropic diffusion (README.md:46, new) */
     KL_OP_DENSE = 3,             /* dense column-major n x n matrix in device memory (`user`), nx = n, ny = 1;
                                     set up by kl_gmres_mgsr_dense / kl_gmres_hh_dense (single GPU only)   */
+    KL_OP_ANISO5_VAR = 4,        /* variable-coefficient anisotropic diffusion, self-adjoint finite-volume form
+                                    (README.md:46 WIP, new): `user` points to a kl_aniso_var_t (single GPU only) */
     KL_OP_USER = 100             /* user callback on device pointers (single GPU only) */
 };
+/* coefficient fields of KL_OP_ANISO5_VAR: cell values kx(i,j), ky(i,j), idx = i + j*nx, DEVICE pointers (kl_vec_alloc /
+ * kl_vec_upload) that stay valid for the duration of the call.  A face carries the mean of its two cells.     */
+typedef struct {
+    const double *kx, *ky;
+} kl_aniso_var_t;
 typedef struct {
     int kind;
     double eps_x, eps_y;  /* KL_OP_ANISO5 */
@@ -212,7 +219,8 @@ int kl_gmres_hh_prec_omp(kl_handle_t h, const kl_operator_t *Ax_vec, const doubl
 int kl_gmres_mgsr_dense(kl_handle_t h, const double *A, int n, const double *b, double *x, int m, double tol,
                         double *final_err, double *v_err, int *n_out, int *restart_out);
 /* gmres_hh_dense(A,b,x,m,tol,final_err,v_err,n_out,stages_out)       src/gmres_hh.f90:10-112
- * (requires m + 1 < n; the reference's `if (j < n)` branch for m >= n is not provided)        */
+ * (m <= n: m = n takes the reference's `if (j < n)` else-branch at the last step; m > n indexes v_j(j) out of
+ * bounds in the reference itself and is rejected)                                                  */
 int kl_gmres_hh_dense(kl_handle_t h, const double *A, int n, const double *b, double *x, int m, double tol,
                       double *final_err, double *v_err, int *n_out, int *stages_out);
 /* hilbert::generate_matrix(H, n)  src/problems/hilbert.f90:6-18: H(i,j) = 1/real(i+j-1), the quotient

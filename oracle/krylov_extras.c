@@ -42,6 +42,36 @@ void ko_aniso(const double *x, double *y, int n)
 }
 ko_stencil_fn ko_get_aniso(void) { return ko_aniso; }
 
+/* ---- anisotropic diffusion with VARIABLE coefficients (README.md:46 WIP; definition ours) --------------
+ * Self-adjoint finite-volume form of  -d/dx(kx du/dx) - d/dy(ky du/dy)  on the unit-spaced grid, zero Dirichlet:
+ * cell coefficients kx(i,j), ky(i,j); a face carries the arithmetic mean of its two cells, a boundary face the
+ * cell's own value.  Evaluation order (shared with the CUDA kernel k_aniso_var, kl_ops.cu):
+ *   wl = 0.5*(kxc + kx(i-1,j))  [kxc at i = 0]   wr = 0.5*(kxc + kx(i+1,j))  [kxc at i = n-1]
+ *   wu = 0.5*(kyc + ky(i,j-1))  [kyc at j = 0]   wd = 0.5*(kyc + ky(i,j+1))  [kyc at j = n-1]
+ *   diag = ((wl + wr) + wd) + wu ; s = fma(wl, xl, wr*xr) ; t = fma(wd, xd, wu*xu) ; y = fma(diag, xc, -(s + t))
+ * missing neighbours count as 0.  ("d" = idx+n, "u" = idx-n, the reference's naming in poisson.f90:42.) */
+static const double *g_kx = NULL, *g_ky = NULL;
+void ko_set_aniso_var(const double *kx, const double *ky) { g_kx = kx; g_ky = ky; }
+void ko_aniso_var(const double *x, double *y, int n)
+{
+    const int64_t N = n;
+    const double *kx = g_kx, *ky = g_ky;
+#pragma omp for collapse(2)
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t i = 0; i < N; ++i) {
+            int64_t idx = i + j * N;
+            double kxc = kx[idx], kyc = ky[idx];
+            double wl = i > 0 ? 0.5 * (kxc + kx[idx - 1]) : kxc, wr = i < N - 1 ? 0.5 * (kxc + kx[idx + 1]) : kxc;
+            double wu = j > 0 ? 0.5 * (kyc + ky[idx - N]) : kyc, wd = j < N - 1 ? 0.5 * (kyc + ky[idx + N]) : kyc;
+            double xl = i > 0 ? x[idx - 1] : 0.0, xr = i < N - 1 ? x[idx + 1] : 0.0;
+            double xd = j < N - 1 ? x[idx + N] : 0.0, xu = j > 0 ? x[idx - N] : 0.0;
+            double diag = ((wl + wr) + wd) + wu;
+            double s = fma(wl, xl, wr * xr), t = fma(wd, xd, wu * xu);
+            y[idx] = fma(diag, x[idx], -(s + t));
+        }
+}
+ko_stencil_fn ko_get_aniso_var(void) { return ko_aniso_var; }
+
 /* ---- degree-k Chebyshev preconditioner (Saad, Alg. 12.1) ---------------
  * params = (eig_a, eig_b) in either order (like cbpr2).
  *   theta = (b+a)/2, delta = |b-a|/2, sigma = theta/delta, rho_0 = 1/sigma

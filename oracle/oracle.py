@@ -95,6 +95,20 @@ def aniso_fn(eps_x: float, eps_y: float):
     return lib().ko_get_aniso()
 
 
+_aniso_var_keep = None
+
+
+def aniso_var_fn(kx: np.ndarray, ky: np.ndarray):
+    """variable-coefficient anisotropic diffusion (krylov_extras.c ko_aniso_var); kx, ky: cell coefficient grids"""
+    global _aniso_var_keep
+    kx = np.ascontiguousarray(kx, dtype=np.float64).reshape(-1)
+    ky = np.ascontiguousarray(ky, dtype=np.float64).reshape(-1)
+    _aniso_var_keep = (kx, ky)
+    lib().ko_set_aniso_var(_p(kx), _p(ky))
+    lib().ko_get_aniso_var.restype = STENCIL_FN
+    return lib().ko_get_aniso_var()
+
+
 def cbpr2_fn():
     return lib().ko_get_cbpr2()
 

@@ -75,7 +75,29 @@ def test_hilbert_drivers(kl, h, ko):
         assert np.abs(g.x - 1).max() < 10 * max(np.abs(o.x - 1).max(), 1e-4)
 
 
+def test_hh_dense_with_m_up_to_n(kl, h, ko):
+    """gmres_hh.f90:53 `if (j < n)`: m = n - 1 builds the last possible reflector, m = n takes the else-branch at
+    j = n (H(j+1,j) = 0, no new reflector).  A generic non-symmetric matrix and tol = 0 force every step to run."""
+    n = 12
+    rng = np.random.default_rng(11)
+    A = 4.0 * np.eye(n) + rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    h.set_option(2, 2)          # two cycles
+    try:
+        for m in (n - 1, n):
+            g = h.gmres_hh_dense(A, b, m, 0.0)
+            o = ko.gmres_hh_dense(A, b, m, 0.0, max_stages=2)
+            assert (g.n_out, g.restart_out) == (o.n_out, o.restart_out) == (m, 2), (m, g.n_out, g.restart_out, o.n_out)
+            k = min(g.history.size, o.history.size, m)
+            assert np.allclose(g.history[:k], o.history[:k], rtol=1e-9, atol=1e-15), m
+            assert np.abs(g.x - o.x).max() < 1e-10 * np.abs(o.x).max()
+            if m == n:
+                assert np.linalg.norm(A @ g.x - b) < 1e-10 * np.linalg.norm(b)      # full Krylov space: exact solve
+    finally:
+        h.set_option(2, 1000)
+
+
 def test_dense_errors(kl, h):
     A = np.eye(8)
     with pytest.raises(kl.KrylovError):
-        h.gmres_hh_dense(A, np.ones(8), 8, 1e-10)      # m + 1 >= n
+        h.gmres_hh_dense(A, np.ones(8), 9, 1e-10)      # m > n: v_j(j) out of bounds in the reference itself

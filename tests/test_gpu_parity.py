@@ -322,6 +322,39 @@ def test_user_operator_callback(kl, h, ko):
     h2.close()
 
 
+def test_variable_coefficient_anisotropic_operator(kl, h, ko):
+    """KL_OP_ANISO5_VAR (README.md:46 "Anisotropic Diffusion Equation (2D) (WIP)"; no reference code, definition in
+    oracle/krylov_extras.c ko_aniso_var): bit-exact against its oracle twin, self-adjoint, equal to the constant-
+    coefficient operator for constant fields, and usable in every solver (generic path)."""
+    ns = 96
+    rng = np.random.default_rng(21)
+    kx = np.exp(rng.uniform(-2.0, 2.0, ns * ns))          # contrast ~ 50
+    ky = 0.01 * np.exp(rng.uniform(-1.0, 1.0, ns * ns))   # anisotropy ~ 100
+    A = kl.aniso_var(kx, ky)
+    Ao = ko.aniso_var_fn(kx, ky)
+    x, y = rng.standard_normal(ns * ns), rng.standard_normal(ns * ns)
+    ax = h.apply(A, x, ns, ns)
+    assert np.array_equal(ax, ko.apply(Ao, x, ns))
+    ay = h.apply(A, y, ns, ns)
+    assert np.dot(ax, y) == pytest.approx(np.dot(x, ay), rel=1e-12)          # <Ax, y> = <x, Ay>
+    assert np.dot(ax, x) > 0                                                  # positive definite
+    ac = h.apply(kl.aniso_var(np.full(ns * ns, 1.0), np.full(ns * ns, 0.01)), x, ns, ns)
+    assert np.allclose(ac, h.apply(kl.aniso(1.0, 0.01), x, ns, ns), rtol=0, atol=1e-14)
+    # manufactured problem x = 1 ; the three solver families against the oracle run on the same operator
+    b = h.apply(A, np.ones(ns * ns), ns, ns)
+    assert np.array_equal(b, ko.manufactured_rhs(Ao, ns))
+    g, o = h.cg_omp(A, b, 1e-9, 20000), ko.cg_omp(Ao, b, 1e-9, 20000)
+    assert g.status == 0 and abs(g.iter - o.iter) <= max(2, o.iter // 100) and np.abs(g.x - 1).max() < 1e-6
+    assert hist_rel(g.history[:50], o.history[:50]) < 1e-10
+    m = 40
+    gg = h.gmres_mgsr_omp(A, b, m, 1e-8, None, None)
+    og = ko.gmres_mgsr_omp(Ao, b, m, 1e-8, ko.identity_fn(), P, max_restarts=1000)
+    assert gg.status == 0 and abs(_its(gg, m) - og.iterations) <= max(1, og.iterations // 100)
+    assert hist_rel(gg.history[:m], og.history[:m]) < 1e-10
+    gb = h.bicgstab(A, b, 1e-9, 20000)
+    assert gb.status == 0 and np.abs(gb.x - 1).max() < 1e-6
+
+
 def test_user_preconditioner_callback(kl, h, ko):
     """procedure(precond) passed by the caller (interfaces.f90:19-28): a Python callback that receives the solver's
     operator A_x, r, z, the solver-owned scratch aux and params -- the reference's dummy-argument list -- and
