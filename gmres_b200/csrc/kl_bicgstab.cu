@@ -254,34 +254,6 @@ struct PBiDir : PwBase<0> {
     }
 };
 
-struct PostBiAlpha {   // :130 alpha = rr0 / ap_r0
-    double *S;
-    __device__ __forceinline__ void run() const { S[S_ALPHA] = S[S_RR] / S[S_RED]; }
-};
-struct PostBiOmega {   // :146 omega = as_s / as_as
-    double *S;
-    __device__ __forceinline__ void run() const { S[S_OMEGA] = S[S_RED] / S[S_RED + 1]; }
-};
-struct PostBiEnd {     // :154-173
-    double *S;
-    int *I;
-    double *hist;
-    int hist_cap;
-    __device__ __forceinline__ void run() const {
-        double res = sqrt(S[S_RED]);
-        double r_r0_new = S[S_RED + 1];
-        S[S_RES] = res;
-        S[S_BETA] = (r_r0_new / S[S_RR]) * (S[S_ALPHA] / S[S_OMEGA]);
-        S[S_RR] = r_r0_new;
-        int it = I[I_ITER] + 1;
-        I[I_ITER] = it;
-        int hl = I[I_HIST];
-        if (hl < hist_cap) hist[hl] = res;
-        I[I_HIST] = hl + 1;
-        if (res < S[S_TOL]) I[I_CONV_AT] = it;
-        else if (!(res == res)) { I[I_BREAKDOWN] = 1; I[I_CONV_AT] = it; }
-    }
-};
 
 static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, int nx, int ny,
                           double tol, int *iter, double *res_out, const kl_precond_t *M,
@@ -297,9 +269,7 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     const int maxit = *iter;
     c->stats = kl_stats_t{};
     prof_reset(c);
-    cudaEvent_t evA, evB;
-    KL_CUDA(c, cudaEventCreate(&evA));
-    KL_CUDA(c, cudaEventCreate(&evB));
+    const cudaEvent_t evA = c->ev2, evB = c->ev3;     // owned by the handle (no leak on the error paths)
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
     KL_TRY(ws_reserve(c, 13 * ws_need(n)));
@@ -471,8 +441,6 @@ static int bicgstab_solve(Ctx *c, const kl_operator_t *A, const double *b, doubl
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);
-    cudaEventDestroy(evA);
-    cudaEventDestroy(evB);
     const int its = c->h_pinned_i[I_ITER];
     c->stats.iterations = its;
     c->stats.cycles = polls;

@@ -24,37 +24,7 @@
 
 namespace kl {
 
-struct PostCgAlpha {  // cg.f90:124-126  alpha = rr / (ax.p)
-    double *S;
-    __device__ __forceinline__ void run() const {
-        S[S_PAP] = S[S_RED];
-        S[S_ALPHA] = S[S_RR] / S[S_RED];
-    }
-};
 
-struct PostCgEnd {
-    double *S;
-    int *I;
-    double *hist;
-    int hist_cap;
-    int precond;  // 0: S_RED[0] = r.r (cg.f90:135-138) ; 1: S_RED[0] = r.z, r.r in S_TMP0 (cg.f90:219-226)
-                  // 2: S_RED[0] = r.r, S_RED[1] = r.z (fused update + preconditioner kernel)
-    __device__ __forceinline__ void run() const {
-        double num = precond == 2 ? S[S_RED + 1] : S[S_RED];
-        double rr2 = precond == 1 ? S[S_TMP0] : S[S_RED];
-        double res = sqrt(rr2);
-        S[S_BETA] = num / S[S_RR];
-        S[S_RR] = num;
-        S[S_RES] = res;
-        int it = I[I_ITER] + 1;
-        I[I_ITER] = it;
-        int hl = I[I_HIST];
-        if (hl < hist_cap) hist[hl] = res;
-        I[I_HIST] = hl + 1;
-        if (res < S[S_TOL]) I[I_CONV_AT] = it;          // cg.f90:144-149
-        else if (!(res == res)) { I[I_BREAKDOWN] = 1; I[I_CONV_AT] = it; }
-    }
-};
 
 // K1 with the deferred x update: x += alpha_prev * p_old ; p_new = z + beta*p_old ; ax = A p_new ; ax.p_new
 // in[0] = z (r for plain CG), in[1] = p_old.  alpha_prev = S[S_ALPHA] of the previous iteration (0 before
@@ -229,9 +199,7 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     const int maxit = *iter;
     c->stats = kl_stats_t{};
     prof_reset(c);
-    cudaEvent_t evA, evB;
-    KL_CUDA(c, cudaEventCreate(&evA));
-    KL_CUDA(c, cudaEventCreate(&evB));
+    const cudaEvent_t evA = c->ev2, evB = c->ev3;     // owned by the handle (no leak on the error paths)
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
@@ -476,8 +444,6 @@ static int cg_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, 
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);
-    cudaEventDestroy(evA);
-    cudaEventDestroy(evB);
     const int its = c->h_pinned_i[I_ITER];
     c->stats.iterations = its;
     c->stats.cycles = polls;

@@ -408,7 +408,6 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     if (f.lo[0] || f.hi[0]) KL_CH_LAUNCH1(OPK, true) else KL_CH_LAUNCH1(OPK, false)
     switch (op->kind) {
         case KL_OP_POISSON5: KL_CH_LAUNCH(KL_OP_POISSON5) break;
-        case KL_OP_POISSON5_BRANCHY: KL_CH_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
         case KL_OP_ANISO5: KL_CH_LAUNCH(KL_OP_ANISO5) break;
         default: return c->fail(KL_ERR_INVALID, "launch_chain: not a built-in operator");
     }
@@ -417,9 +416,10 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     c->stats.kernel_launches++;
     // the post functor (scalar recurrences on the reduced sums) runs in its own one-warp kernel: the chain
     // kernels are not templated on it (each instantiation is 6 phases x L levels of code)
-    if (C::NRED > 0 && !std::is_same<Post, NoPost>::value) {
-        if (c->nranks > 1) return finish_reduction(c, C::NRED, post, f.flags, f.step, f.run_on_conv);
-        k_post<Post><<<1, 32, 0, c->stream>>>(post, f.flags, f.step, f.run_on_conv);
+    const PostAny pa = to_any(post);
+    if (C::NRED > 0 && pa.kind != PK_NoPost) {
+        if (c->nranks > 1) return finish_reduction(c, C::NRED, pa, f.flags, f.step, f.run_on_conv);
+        k_post<<<1, 32, 0, c->stream>>>(pa, f.flags, f.step, f.run_on_conv);
         c->stats.kernel_launches++;
     }
     return KL_OK;

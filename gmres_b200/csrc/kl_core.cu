@@ -511,6 +511,7 @@ int kl_create(kl_handle_t *h, int device) {
     ok = ok && cudaMallocHost(&c->h_pinned, sizeof(double) * S_COUNT) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_pinned_i, sizeof(int) * I_COUNT) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess;
     if (ok) {
         ok = cudaMemset(c->d_S, 0, sizeof(double) * S_COUNT) == cudaSuccess &&
              cudaMemset(c->d_I, 0, sizeof(int) * I_COUNT) == cudaSuccess &&
@@ -546,6 +547,8 @@ int kl_destroy(kl_handle_t h) {
     if (c->h_pinned_i) cudaFreeHost(c->h_pinned_i);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
     prof_reset(c);
     graph_clear(c);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);

@@ -248,14 +248,6 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
     }
 }
 
-struct PostBeta {   // gmres_mgsr.f90:322-323  beta = norm2(w) ; g(1) = beta
-    GmresDev G;
-    __device__ __forceinline__ void run() const {
-        double beta = sqrt(G.S[S_RED]);
-        G.S[S_NORM] = beta;
-        G.g[0] = beta;
-    }
-};
 
 // ---- back substitution by one warp (gmres_mgsr.f90:394-398) -------------------
 // lane 0 runs the reference's sequential recurrence; the warp stages row i of H.
@@ -369,9 +361,14 @@ int launch_vtw(Ctx *c, const double *V, size_t ldv, const double *w, size_t n, i
     return KL_OK;
 }
 
-bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc) {
-    return c->opt_tma && nc >= 1 && nc <= kTsWarps * kTsCpw && n % 2 == 0 && ldv % 2 == 0 && n >= 4096 &&
-           n < (size_t)1 << 31;
+// Can the TMA tall-skinny kernels run?  EVERY rank must take the same decision (the two paths all-reduce different
+// numbers of values and only one of them can skip the second pass), so on several ranks it is taken from the global
+// grid and the smallest / largest slab of the partition, never from this rank's own n.
+bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc, int nx, int ny) {
+    if (!(c->opt_tma && nc >= 1 && nc <= kTsWarps * kTsCpw && ldv % 2 == 0)) return false;
+    if (c->nranks == 1 || nx <= 0) return n % 2 == 0 && n >= 4096 && n < (size_t)1 << 31;
+    const size_t n_min = (size_t)nx * (size_t)(ny / c->nranks), n_max = (size_t)nx * (size_t)((ny + c->nranks - 1) / c->nranks);
+    return nx % 2 == 0 && n_min >= 4096 && n_max < (size_t)1 << 31;
 }
 
 int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
@@ -467,9 +464,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     const int vec = (n % 2 == 0) ? 2 : 1;
     c->stats = kl_stats_t{};
     prof_reset(c);
-    cudaEvent_t evA, evB;
-    KL_CUDA(c, cudaEventCreate(&evA));
-    KL_CUDA(c, cudaEventCreate(&evB));
+    const cudaEvent_t evA = c->ev2, evB = c->ev3;     // owned by the handle (no leak on the error paths)
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
@@ -591,7 +586,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
                 }
                 bytes += (32.0 * total + 24.0) * n;
             } else {
-                if (c->opt_ortho == KL_ORTHO_CGS2_SELECTIVE && ts_tma_ok(c, n, ldv, ncols)) {
+                if (c->opt_ortho == KL_ORTHO_CGS2_SELECTIVE && ts_tma_ok(c, n, ldv, ncols, P.nx, P.ny)) {
                     const double eta = c->opt_reorth_eta_permille * 1e-3;
                     { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
                       KL_TRY(launch_ts_tma(c, false, V, ldv, m + 1, wj, n, ncols, nullptr, G.hvec, G, j, 1, true, 0)); }
@@ -602,7 +597,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
                     { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
                       KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec2, true, G, j, true, true, true)); }
                     bytes += (24.0 * ncols + 40.0) * n;
-                } else if (ts_tma_ok(c, n, ldv, ncols)) {
+                } else if (ts_tma_ok(c, n, ldv, ncols, P.nx, P.ny)) {
                     // 3 passes over V: project ; update + project (fused, V tile staged once) ; update + norm
                     { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
                       KL_TRY(launch_ts_tma(c, false, V, ldv, m + 1, wj, n, ncols, nullptr, G.hvec, G, j, 1, true)); }
@@ -724,8 +719,6 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);
-    cudaEventDestroy(evA);
-    cudaEventDestroy(evB);
     c->stats.iterations = c->h_pinned_i[I_ITER];
     c->stats.cycles = cycles;
     c->stats.solve_ms = ms;

@@ -12,16 +12,6 @@ constexpr int kTsCpw = 12;          // columns per warp per pass
 constexpr int kTsU = 4;             // row chunks per lane per trip
 constexpr int kTsMaxBlocks = 1024;  // partials leading dimension
 
-struct GmresDev {
-    double *H;      // (m+1) x m, ldh = m+1
-    double *g, *cs, *sn, *y, *fe, *hvec, *hvec2;
-    double *S;
-    int *I;
-    double *hist;
-    int hist_cap;
-    int m, ldh;
-    int mf;         // 1: gmres_mgsr_mf semantics (h_val < tol also stops; :172)
-};
 
 // ---- Givens update by ONE WARP (gmres_mgsr.f90:362-389) --------------------
 // hj1 = H(j+1,j) (||w|| after orthogonalisation for MGS, -/+||w(j+1:n)|| for
@@ -112,23 +102,13 @@ struct PMgsStep : PwBase<1> {
         }
     }
 };
-struct PostMgs {
-    GmresDev G;
-    int j, i_cur;
-    __device__ __forceinline__ void run() const {
-        double h = G.S[S_RED];
-        G.S[S_TMP0] = h;
-        double *Hj = G.H + (size_t)j * G.ldh;
-        Hj[i_cur] = Hj[i_cur] + h;
-    }
-};
 
 // host launchers implemented in kl_gmres.cu
 int launch_vtw(Ctx *c, const double *V, size_t ldv, const double *w, size_t n, int ncols, double *out,
                const GmresDev &G, int j, int h_mode, bool gated);
 int launch_backsolve(Ctx *c, const GmresDev &G);
 // TMA-staged projection (update = false) or update + second projection (update = true)
-bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc);
+bool ts_tma_ok(Ctx *c, size_t n, size_t ldv, int nc, int nx = 0, int ny = 0);
 int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
                   const double *h_in, double *out, const GmresDev &G, int j, int h_mode, bool gated,
                   long long tail0 = -1, const double *tail_T = nullptr, double *tail_tvec = nullptr, int tail_ldt = 0);

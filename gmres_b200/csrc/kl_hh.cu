@@ -23,10 +23,6 @@
 
 namespace kl {
 
-struct PostHh {   // S_TMP0 = 2 * dot   (the "2.0d0*P*dot" factor of gmres_hh.f90:280)
-    double *S;
-    __device__ __forceinline__ void run() const { S[S_TMP0] = 2.0 * S[S_RED]; }
-};
 
 // v = e_j - 2 P_j (P_j . e_j) fused with the dot against the next reflector
 // (gmres_hh.f90:257-283, first trip of the i-loop).
@@ -453,9 +449,7 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
     const int ldh = m + 1;
     c->stats = kl_stats_t{};
     prof_reset(c);
-    cudaEvent_t evA, evB;
-    KL_CUDA(c, cudaEventCreate(&evA));
-    KL_CUDA(c, cudaEventCreate(&evB));
+    const cudaEvent_t evA = c->ev2, evB = c->ev3;     // owned by the handle (no leak on the error paths)
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
     size_t need = ws_need(ldv * (size_t)(m + 1)) + (c->opt_verr ? ws_need(ldv * (size_t)m) : 0) + 7 * ws_need(n) +
@@ -733,8 +727,6 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
     float ms = 0, ms_tot = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     cudaEventElapsedTime(&ms_tot, evA, evB);
-    cudaEventDestroy(evA);
-    cudaEventDestroy(evB);
     c->stats.iterations = c->h_pinned_i[I_ITER];
     c->stats.cycles = cycles;
     c->stats.solve_ms = ms;

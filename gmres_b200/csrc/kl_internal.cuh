@@ -56,6 +56,10 @@ enum IIdx {
     I_COUNT = 64
 };
 
+}  // namespace kl
+#include "kl_posts.cuh"
+namespace kl {
+
 // NVLink peer-memory communication buffer (one per rank, mapped into every process through CUDA IPC); layout in
 // doubles.  Used by the stand-alone collectives in kl_core.cu and by the all-reduce that the LAST BLOCK of a
 // reducing kernel performs inline (peer_allreduce_block below).
@@ -175,7 +179,8 @@ struct kl_context_s {
     kl_stats_t stats{};
     std::vector<double> history;
     int history_len = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // iteration loop
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // whole call (incl. host<->device copies)
     // TMA descriptor cache (opaque 128-byte CUtensorMap blobs keyed by base pointer and extents)
     struct TmapEntry { const void *base; int nx, ny; long long k1 = 0, k2 = 0; alignas(64) unsigned char blob[128]; };
     std::vector<TmapEntry> tmaps;
@@ -444,6 +449,13 @@ __device__ __forceinline__ double apply5(double c, double l, double r, double dn
     }
 }
 
+// the same with the operator chosen at run time (generic, non-TMA kernel: small and odd grids, KL_OPT_TMA = 0)
+__device__ __forceinline__ double apply5_rt(int opk, double c, double l, double r, double dn, double up, const OpCoef &k) {
+    if (opk == KL_OP_POISSON5) return apply5<KL_OP_POISSON5>(c, l, r, dn, up, k);
+    if (opk == KL_OP_POISSON5_BRANCHY) return apply5<KL_OP_POISSON5_BRANCHY>(c, l, r, dn, up, k);
+    return apply5<KL_OP_ANISO5>(c, l, r, dn, up, k);
+}
+
 // ------------------------------------------------------------------------
 // Marching stencil kernel framework.
 //
@@ -518,9 +530,9 @@ constexpr int kStencilThreads = 128;
 // independent 16-byte loads in flight; point() runs when a line is consumed.
 constexpr int kPf = 2;   // prefetch distance in grid lines
 
-template <class F, int OPK, int VEC, class Post>
+template <class F, int VEC>
 __global__ void __launch_bounds__(kStencilThreads)
-k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post) {
+k_stencil(const F f_in, const Geo g, const RedCtl rc, const PostAny post, const int fuse_post, const int opk) {
     griddep_wait();
     griddep_launch();
     if (f_in.skip()) return;
@@ -620,10 +632,10 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
         if (act) {
             double au[VEC];
             if (VEC == 1) {
-                au[0] = apply5<OPK>(cu[0], l, r, dn[0], up[0], f.coef);
+                au[0] = apply5_rt(opk, cu[0], l, r, dn[0], up[0], f.coef);
             } else {
-                au[0] = apply5<OPK>(cu[0], l, cu[VEC - 1], dn[0], up[0], f.coef);
-                au[VEC - 1] = apply5<OPK>(cu[VEC - 1], cu[0], r, dn[VEC - 1], up[VEC - 1], f.coef);
+                au[0] = apply5_rt(opk, cu[0], l, cu[VEC - 1], dn[0], up[0], f.coef);
+                au[VEC - 1] = apply5_rt(opk, cu[VEC - 1], cu[0], r, dn[VEC - 1], up[VEC - 1], f.coef);
             }
             if constexpr (F::kPush)
                 f.template store<VEC>((size_t)j * g.nx + i0, rawCu.c, cu, au, acc, (j == 0 ? 1 : 0) | (j == g.ny - 1 ? 2 : 0));
@@ -659,9 +671,9 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const Post post, const int
 // ------------------------------------------------------------------------
 constexpr int kPwThreads = 256;
 
-template <class F, int VEC, class Post>
+template <class F, int VEC>
 __global__ void __launch_bounds__(kPwThreads)
-k_pointwise(const F f_in, const size_t n, const RedCtl rc, const Post post, const int fuse_post) {
+k_pointwise(const F f_in, const size_t n, const RedCtl rc, const PostAny post, const int fuse_post) {
     griddep_wait();
     if (f_in.skip()) return;
     F f = f_in;
@@ -699,13 +711,9 @@ struct PwBase {
     }
 };
 
-struct NoPost {
-    __device__ __forceinline__ void run() const {}
-};
 
 // post functor launched on its own (multi-GPU: after the all-reduce)
-template <class Post>
-__global__ void k_post(const Post post, const int *flags, const int step, const int run_on_conv) {
+static __global__ void k_post(const PostAny post, const int *flags, const int step, const int run_on_conv) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (flags) {   // same gate as the kernel whose sums it consumes
             const int ca = flags[I_CONV_AT];
@@ -745,7 +753,7 @@ inline int finish_reduction(Ctx *c, int nred, const Post &post, const int *flags
                             int run_on_conv = 0) {
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, c->d_S + S_RED, nred));
-        k_post<Post><<<1, 32, 0, c->stream>>>(post, flags, step, run_on_conv);
+        k_post<<<1, 32, 0, c->stream>>>(to_any(post), flags, step, run_on_conv);
         c->stats.kernel_launches++;
     }
     return KL_OK;
@@ -831,6 +839,8 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     RedCtl rc = redctl(c);
     const bool inl = F::NRED > 0 && redctl_inline_allreduce(c, rc, F::NRED);
     const int fuse = c->nranks == 1 || inl;
+    const PostAny pa = to_any(post);
+    const int opk = op->kind;
     TMaps<F::NIN> tm;
     if (tma) {
         for (int a = 0; a < F::NIN; ++a) KL_TRY(tmap_encode(c, &tm.m[a], f.in[a], nx, ny));
@@ -862,24 +872,27 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
         cfg.gridDim = grid;                                                                         \
         cfg.dynamicSmemBytes = SMEM;                                                                \
     }
-#define KL_ST_LAUNCH(OPK)                                                                           \
-    if (tma) {                                                                                      \
-        KL_ST_GEO((k_stencil_tma<F, OPK, Post>), smem)                                              \
-        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil_tma<F, OPK, Post>, f, g, rc, post, fuse, tm)); \
-    } else if (vec == 2) {                                                                          \
-        KL_ST_GEO((k_stencil<F, OPK, 2, Post>), 0)                                                  \
-        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, OPK, 2, Post>, f, g, rc, post, fuse));     \
-    } else {                                                                                        \
-        KL_ST_GEO((k_stencil<F, OPK, 1, Post>), 0)                                                  \
-        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, OPK, 1, Post>, f, g, rc, post, fuse));     \
+    if (opk != KL_OP_POISSON5 && opk != KL_OP_POISSON5_BRANCHY && opk != KL_OP_ANISO5)
+        return c->fail(KL_ERR_INVALID, "launch_stencil: not a built-in operator");
+    // the TMA kernel is specialised per operator (its inner loop is the hot path); the generic kernel takes it as
+    // a run-time argument
+#define KL_ST_TMA(OPK)                                                                              \
+    {                                                                                               \
+        KL_ST_GEO((k_stencil_tma<F, OPK>), smem)                                                    \
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil_tma<F, OPK>, f, g, rc, pa, fuse, tm));        \
     }
-    switch (op->kind) {
-        case KL_OP_POISSON5: KL_ST_LAUNCH(KL_OP_POISSON5) break;
-        case KL_OP_POISSON5_BRANCHY: KL_ST_LAUNCH(KL_OP_POISSON5_BRANCHY) break;
-        case KL_OP_ANISO5: KL_ST_LAUNCH(KL_OP_ANISO5) break;
-        default: return c->fail(KL_ERR_INVALID, "launch_stencil: not a built-in operator");
+    if (tma) {
+        if (opk == KL_OP_POISSON5) KL_ST_TMA(KL_OP_POISSON5)
+        else if (opk == KL_OP_POISSON5_BRANCHY) KL_ST_TMA(KL_OP_POISSON5_BRANCHY)
+        else KL_ST_TMA(KL_OP_ANISO5)
+    } else if (vec == 2) {
+        KL_ST_GEO((k_stencil<F, 2>), 0)
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, 2>, f, g, rc, pa, fuse, opk));
+    } else {
+        KL_ST_GEO((k_stencil<F, 1>), 0)
+        KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil<F, 1>, f, g, rc, pa, fuse, opk));
     }
-#undef KL_ST_LAUNCH
+#undef KL_ST_TMA
 #undef KL_ST_GEO
     c->stats.kernel_launches++;
     if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
@@ -899,10 +912,11 @@ inline int launch_pointwise(Ctx *c, F f, size_t n, const Post &post) {
     RedCtl rc = redctl(c);
     const bool inl = F::NRED > 0 && redctl_inline_allreduce(c, rc, F::NRED);
     const int fuse = c->nranks == 1 || inl;
+    const PostAny pa = to_any(post);
     if (n % 2 == 0)
-        k_pointwise<F, 2, Post><<<pw_grid(n / 2), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
+        k_pointwise<F, 2><<<pw_grid(n / 2), kPwThreads, 0, c->stream>>>(f, n, rc, pa, fuse);
     else
-        k_pointwise<F, 1, Post><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, post, fuse);
+        k_pointwise<F, 1><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, pa, fuse);
     c->stats.kernel_launches++;
     if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;

@@ -17,7 +17,6 @@
 
 namespace kl {
 
-constexpr int kLanMax = 256;
 
 struct PLanUpdate : PwBase<1> {
     double *w;
@@ -46,23 +45,6 @@ struct PLanUpdate : PwBase<1> {
             acc[0] = fma(vw[e], vw[e], acc[0]);
         }
         KL_ST(VEC, w, i, vw)
-    }
-};
-struct PostLanAlpha {
-    double *S;
-    int step;
-    __device__ __forceinline__ void run() const { S[S_LAN + step] = S[S_RED]; }
-};
-struct PostLanBeta {
-    double *S;
-    int *I;
-    int step;
-    __device__ __forceinline__ void run() const {
-        double bt = sqrt(S[S_RED]);
-        S[S_LAN + kLanMax + step] = bt;
-        S[S_NORM] = bt;
-        I[I_ITER] = step + 1;
-        if (!(bt > 0.0)) I[I_CONV_AT] = step;
     }
 };
 struct PFill : PwBase<0> {

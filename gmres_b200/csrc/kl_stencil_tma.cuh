@@ -75,9 +75,9 @@ __device__ __forceinline__ unsigned smid() {
 }
 #endif
 
-template <class F, int OPK, class Post>
+template <class F, int OPK>
 __global__ void __launch_bounds__(kStencilThreads)
-k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const Post post, const int fuse_post,
+k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, const int fuse_post,
               const __grid_constant__ TMaps<F::NIN> tm) {
     // programmatic dependent launch (see griddep_wait): kLateWait functors run their whole prologue, the first TMA
     // stages and the first lines of u before they need anything the preceding kernel produces
