@@ -94,6 +94,7 @@ def load_library():
         getattr(L, name).argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.kl_destroy.argtypes = [C.c_void_p]
     L.kl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.kl_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.kl_synchronize.argtypes = [C.c_void_p]
     L.kl_set_pointer_mode.argtypes = [C.c_void_p, C.c_int]
     L.kl_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -276,8 +277,8 @@ class Handle:
                               "(this library has no CPU path)")
         self.device = int(device)
         self.rank, self.nranks = 0, 1
-        self._user_stream = stream is not None     # an explicitly chosen stream is never rebound
-        self._bound_stream = None
+        self._user_stream = stream is not None
+        self._bound_stream = None                  # (pointer, torch ExternalStream) of the handle's stream
         if stream is not None:
             self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream)))
 
@@ -311,23 +312,34 @@ class Handle:
         self.set_option(KL_OPT_ORTHO, mode)
 
     def set_stream(self, stream: Optional[int]):
-        """Run on an existing CUDA stream (None: the handle's own stream).  With an explicit stream the caller
-        orders the handle's work against the producers / consumers of device-resident vectors."""
+        """Run on an existing CUDA stream (None: the handle's own stream).  Device-pointer calls are ordered against
+        torch's current stream with events either way (_order_in / _order_out)."""
         self._chk(self._L.kl_set_stream(self._h, C.c_void_p(stream or 0)))
         self._user_stream = stream is not None
         self._bound_stream = None
 
-    def _bind_torch_stream(self):
-        """Device-pointer mode: enqueue on torch's CURRENT stream, so that the library's kernels are ordered after
-        whatever produced the input tensors and before whatever consumes (or frees) the outputs.  The handle's
-        own stream is cudaStreamNonBlocking and would not synchronise with torch's streams at all."""
-        if self._user_stream:
-            return
+    def _lib_stream(self):
+        """the handle's stream as a torch.cuda.ExternalStream (for event-based ordering)"""
         import torch
-        s = torch.cuda.current_stream(self.device).cuda_stream or 1     # 0 = legacy default stream = cudaStreamLegacy (0x1)
-        if s != self._bound_stream:
-            self._chk(self._L.kl_set_stream(self._h, C.c_void_p(s)))
-            self._bound_stream = s
+        p = C.c_void_p()
+        self._chk(self._L.kl_get_stream(self._h, C.byref(p)))
+        if self._bound_stream is None or self._bound_stream[0] != (p.value or 0):
+            self._bound_stream = (p.value or 0, torch.cuda.ExternalStream(p.value or 0, device=torch.device("cuda", self.device)))
+        return self._bound_stream[1]
+
+    def _order_in(self):
+        """Device-pointer mode: the library's stream (cudaStreamNonBlocking, it does not synchronise with torch's
+        streams by itself) waits for everything already enqueued on torch's CURRENT stream -- the producers of the
+        input tensors.  Kernels still run on the handle's own stream (running them on torch's legacy default
+        stream cost the fused CG kernels their programmatic-dependent-launch overlap)."""
+        import torch
+        self._lib_stream().wait_stream(torch.cuda.current_stream(self.device))
+
+    def _order_out(self):
+        """... and torch's current stream waits for the library's work, so that consumers of the outputs (and the
+        caching allocator, when an input tensor is freed right after the call) are ordered after it."""
+        import torch
+        torch.cuda.current_stream(self.device).wait_stream(self._lib_stream())
 
     def synchronize(self):
         self._chk(self._L.kl_synchronize(self._h))
@@ -379,7 +391,7 @@ class Handle:
             import torch
             assert a.dtype == torch.float64 and a.is_contiguous()
             self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_DEVICE))
-            self._bind_torch_stream()
+            self._order_in()
             return a, C.c_void_p(a.data_ptr()), True
         arr = np.ascontiguousarray(a, dtype=np.float64)
         self._chk(self._L.kl_set_pointer_mode(self._h, KL_POINTER_HOST))
@@ -419,6 +431,8 @@ class Handle:
         y, yp = self._out_like(xa, dev)
         o, keep = A._c()
         self._chk(self._L.kl_apply_operator(self._h, C.byref(o), xp, yp, nx, ny))
+        if dev:
+            self._order_out()
         return y
 
     def apply_precond(self, M: Precond, A: Operator, r, params: Sequence[float], nx: int, ny: int):
@@ -430,6 +444,8 @@ class Handle:
         pr = np.ascontiguousarray(params, dtype=np.float64)
         self._chk(self._L.kl_apply_precond(self._h, C.byref(p), C.byref(o), rp, zp,
                                            pr.ctypes.data_as(_dp), pr.size, nx, ny))
+        if dev:
+            self._order_out()
         return z
 
     # -- GMRES
@@ -448,6 +464,8 @@ class Handle:
             pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
             args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
         rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        if dev:
+            self._order_out()
         return GmresResult(x, fe, ve, n_out.value, rs.value, rc, self.history(), self.stats())
 
     def gmres_mgsr_omp(self, Ax_vec, b, m, tol, M_inv=None, params=None, nx=None, ny=None):
@@ -487,6 +505,8 @@ class Handle:
         Aa, Ap = self._dense_in(A, n)
         y, yp = self._out_like(xa, dev)
         self._chk(self._L.kl_dense_matvec(self._h, Ap, n, xp, yp))
+        if dev:
+            self._order_out()
         return y
 
     def _gmres_dense(self, fn, A, b, m, tol):
@@ -500,6 +520,8 @@ class Handle:
         rc = self._chk(fn(self._h, Ap, n, bp, xp, int(m), float(tol), fe.ctypes.data_as(_dp),
                           ve.ctypes.data_as(_dp), C.byref(n_out), C.byref(rs)),
                        allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        if dev:
+            self._order_out()
         return GmresResult(x, fe, ve, n_out.value, rs.value, rc, self.history(), self.stats())
 
     def gmres_mgsr_dense(self, A, b, m, tol):
@@ -521,6 +543,8 @@ class Handle:
             pr = np.ascontiguousarray(params if params is not None else (0.0, 0.0), dtype=np.float64)
             args += [C.byref(p), pr.ctypes.data_as(_dp), pr.size]
         rc = self._chk(fn(*args), allow=(KL_OK, KL_NOT_CONVERGED, KL_BREAKDOWN))
+        if dev:
+            self._order_out()
         return CgResult(x, itc.value, res.value, rc, self.history(), self.stats())
 
     def cg(self, Ax_op, b, tol, iter, nx=None, ny=None):

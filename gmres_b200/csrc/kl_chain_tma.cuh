@@ -307,10 +307,13 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         }
     };
 
-    // one stage boundary check + step, phase PH
-    auto phase = [&](auto ph, const int t) {
+    // one stage boundary check + step, phase PH.  CHECK = false: the step is known to exist (whole hexads of the
+    // main loop) -- no per-step bound test, so the march body is straight-line code and the shuffles need no
+    // reconvergence scaffolding (WARPSYNC / ENDCOLLECTIVE around every SHFL of a conditionally executed step)
+    auto phase = [&](auto ph, auto chk, const int t) {
         constexpr int PH = decltype(ph)::value;
-        if (t < T) {
+        constexpr bool CHECK = decltype(chk)::value;
+        if (!CHECK || t < T) {
             if (PH % SR == 0) mbar_wait(&full[q % NST], (unsigned)((q / NST) & 1));
             step(ph, t);
             if (PH % SR == SR - 1) {
@@ -329,19 +332,31 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             }
         }
     };
+    using TT = std::true_type;
+    using FF = std::false_type;
 
     int hs = 0;   // ring line of the current hexad
-    for (int t0 = 0; t0 < T; t0 += 6) {
+    int t0 = 0;
+    for (; t0 + 6 <= T; t0 += 6) {
         cur = tb + (size_t)hs * BWP;
         prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
-        phase(std::integral_constant<int, 0>{}, t0 + 0);
-        phase(std::integral_constant<int, 1>{}, t0 + 1);
-        phase(std::integral_constant<int, 2>{}, t0 + 2);
-        phase(std::integral_constant<int, 3>{}, t0 + 3);
-        phase(std::integral_constant<int, 4>{}, t0 + 4);
-        phase(std::integral_constant<int, 5>{}, t0 + 5);
+        phase(std::integral_constant<int, 0>{}, FF{}, t0 + 0);
+        phase(std::integral_constant<int, 1>{}, FF{}, t0 + 1);
+        phase(std::integral_constant<int, 2>{}, FF{}, t0 + 2);
+        phase(std::integral_constant<int, 3>{}, FF{}, t0 + 3);
+        phase(std::integral_constant<int, 4>{}, FF{}, t0 + 4);
+        phase(std::integral_constant<int, 5>{}, FF{}, t0 + 5);
         hs += 6;
         if (hs == NR) hs = 0;
+    }
+    if (t0 < T) {      // the last, partial hexad
+        cur = tb + (size_t)hs * BWP;
+        prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
+        phase(std::integral_constant<int, 0>{}, TT{}, t0 + 0);
+        phase(std::integral_constant<int, 1>{}, TT{}, t0 + 1);
+        phase(std::integral_constant<int, 2>{}, TT{}, t0 + 2);
+        phase(std::integral_constant<int, 3>{}, TT{}, t0 + 3);
+        phase(std::integral_constant<int, 4>{}, TT{}, t0 + 4);
     }
 
     if (NRED > 0) {
@@ -378,8 +393,9 @@ inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid) {
     return true;
 }
 
+// red_src: which of the kernel's reductions the post functor consumes (it reads S_RED[0])
 template <class C, class Post>
-inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, const Post &post) {
+inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, const Post &post, int red_src = 0) {
     constexpr int L = C::L;
     using D = ChainDims<L>;
     using RG = ChainRing<C>;
@@ -418,8 +434,8 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     // kernels are not templated on it (each instantiation is 6 phases x L levels of code)
     const PostAny pa = to_any(post);
     if (C::NRED > 0 && pa.kind != PK_NoPost) {
-        if (c->nranks > 1) return finish_reduction(c, C::NRED, pa, f.flags, f.step, f.run_on_conv);
-        k_post<<<1, 32, 0, c->stream>>>(pa, f.flags, f.step, f.run_on_conv);
+        if (c->nranks > 1) return finish_reduction(c, C::NRED, pa, f.flags, f.step, f.run_on_conv, red_src);
+        k_post<<<1, 32, 0, c->stream>>>(pa, f.flags, f.step, f.run_on_conv, c->d_S + S_RED, red_src);
         c->stats.kernel_launches++;
     }
     return KL_OK;
@@ -431,21 +447,21 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
 // Same arithmetic per point as FChebStep (kl_ops.cuh) => bit-identical results.
 // mode 0: no reduction ; 1: acc0 = sum z*z ; 2: acc0 = sum r*z
 // ---------------------------------------------------------------------------
+// Reductions: acc0 = sum z*z and acc1 = sum r*z are BOTH kept (two DFMA per point instead of two DFMA and four
+// selects on a run-time mode); the launcher tells the post functor which one to read (launch_chain red_src).
 template <int L_>
-struct ChCheb : ChainBase<1, L_, 1, 1> {
+struct ChCheb : ChainBase<1, L_, 1, 2> {
     double *z, *d_out;     // d_out != nullptr: also store d_L (continuation with FChebStep for degrees > kChainMaxL)
-    int mode;
+    int mode;              // 0: the sums are not used ; 1: z.z ; 2: r.z   (host side only)
     double theta;
     double c1[L_], c2[L_];
     FastDiv fd;
     __device__ __forceinline__ void init() { fd.set(theta); }
     __device__ __forceinline__ void level0(bool, size_t, const double (&raw)[1][2], double (&u)[2],
                                            double (&cc)[1][2], double *) const {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            u[e] = fd.div(raw[0][e]);
-            cc[0][e] = u[e];
-        }
+        fd.div2(raw[0][0], raw[0][1], u[0], u[1]);
+        cc[0][0] = u[0];
+        cc[0][1] = u[1];
     }
     template <class RAW>
     __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
@@ -464,8 +480,8 @@ struct ChCheb : ChainBase<1, L_, 1, 1> {
             if (d_out) stg2(d_out + idx, cout[0][0], cout[0][1]);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                if (mode == 1) acc[0] = fma(u[e], u[e], acc[0]);
-                if (mode == 2) acc[0] = fma(r2[e], u[e], acc[0]);
+                acc[0] = fma(u[e], u[e], acc[0]);
+                acc[1] = fma(r2[e], u[e], acc[1]);
             }
         }
     }
@@ -475,7 +491,7 @@ struct ChCheb : ChainBase<1, L_, 1, 1> {
 //   in[0] = z_{s0}, in[1] = d_{s0}, in[2] = r ;  level 0: u = z, d = d ;  level l as above ;  z = u_L
 // z and d are read with the CTA's halo lines, so the outputs must be other buffers than the inputs.
 template <int L_>
-struct ChChebCont : ChainBase<3, L_, 1, 1> {
+struct ChChebCont : ChainBase<3, L_, 1, 2> {
     static constexpr int SR = 2, NST = 6;                 // 12-line ring: keeps up to 6 lines behind the march
     static constexpr int MINB = L_ <= 4 ? 3 : 2;          // 74 KB of ring per CTA: 3 CTAs per SM at most
     double *z;
@@ -506,8 +522,8 @@ struct ChChebCont : ChainBase<3, L_, 1, 1> {
             stg2(z + idx, u[0], u[1]);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                if (mode == 1) acc[0] = fma(u[e], u[e], acc[0]);
-                if (mode == 2) acc[0] = fma(r2[e], u[e], acc[0]);
+                acc[0] = fma(u[e], u[e], acc[0]);
+                acc[1] = fma(r2[e], u[e], acc[1]);
             }
         }
     }

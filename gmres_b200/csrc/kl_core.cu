@@ -576,6 +576,12 @@ int kl_set_stream(kl_handle_t h, void *cuda_stream) {
     return KL_OK;
 }
 
+int kl_get_stream(kl_handle_t h, void **cuda_stream) {
+    if (!h || !cuda_stream) return KL_ERR_INVALID;
+    *cuda_stream = (void *)h->stream;
+    return KL_OK;
+}
+
 int kl_synchronize(kl_handle_t h) {
     if (!h) return KL_ERR_INVALID;
     KL_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -323,15 +323,18 @@ __global__ void k_hh_first_wy(const GmresDev G, const HhWy W, const double *w) {
 // serial block of the reference in WY form: H(:,j), Householder pivot, new column of Ytop and of T
 // (8 warps), then the Givens update by warp 0 (gmres_hh.f90:305-345).  u = Y^T w (u[0..j]) and the
 // tail sum u[j+1].
-__global__ void __launch_bounds__(256)
+constexpr int kHhStepThreads = 1024;     // 32 warps: the O(j^2) triangular products are latency-bound chains of
+                                          // L2 loads, one output element per warp -- more warps, fewer rounds
+__global__ void __launch_bounds__(kHhStepThreads)
 k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, const int j, const int prec_variant) {
     extern __shared__ double sm[];     // 3*(m+2) for Givens + (m+2) for z
     if (G.I[I_CONV_AT] >= 0) return;
+    constexpr int NW = kHhStepThreads / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *sh = sm, *sz = sm + 3 * (G.m + 2);
     __shared__ double s_sc[3];
     double *Hj = G.H + (size_t)j * G.ldh;
-    for (int i = threadIdx.x; i <= j; i += 256) {          // :306 H(1:j,j) = w(1:j)
+    for (int i = threadIdx.x; i <= j; i += kHhStepThreads) {          // :306 H(1:j,j) = w(1:j)
         const double t = w[i];
         sh[i] = t;
         Hj[i] = t;
@@ -350,10 +353,10 @@ k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, c
     __syncthreads();
     const double hj1 = s_sc[0], pv = s_sc[1], nw = s_sc[2];
     // Ytop(:, j+1) = masked w / nw
-    for (int r = threadIdx.x; r <= G.m; r += 256)
+    for (int r = threadIdx.x; r <= G.m; r += kHhStepThreads)
         W.Ytop[(size_t)(j + 1) * W.ldy + r] = r <= j ? 0.0 : ((r == j + 1 ? pv : w[r]) / nw);
     // z = Y^T p_{j+1} = (u - sum_{r<=j} Ytop(r,:) w_r - Ytop(j+1,:) hj1) / nw
-    for (int c = wid; c <= j; c += 8) {
+    for (int c = wid; c <= j; c += NW) {
         double t = 0.0;
         for (int r = c + lane; r <= j; r += 32) t = fma(W.Ytop[(size_t)c * W.ldy + r], sh[r], t);
         t = warp_sum(t);
@@ -361,7 +364,7 @@ k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, c
     }
     __syncthreads();
     // T(0..j, j+1) = -2 T z ; T(j+1,j+1) = 2
-    for (int r = wid; r <= j; r += 8) {
+    for (int r = wid; r <= j; r += NW) {
         double t = 0.0;
         for (int c = r + lane; c <= j; c += 32) t = fma(W.T[(size_t)c * W.ldt + r], sz[c], t);
         t = warp_sum(t);
@@ -373,7 +376,7 @@ k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, c
     __syncthreads();
     if (j + 1 < G.m) {
         const int jn = j + 1;
-        for (int r = wid; r <= jn; r += 8) {
+        for (int r = wid; r <= jn; r += NW) {
             double t = 0.0;
             for (int c = r + lane; c <= jn; c += 32) t = fma(W.T[(size_t)c * W.ldt + r], W.Ytop[(size_t)c * W.ldy + jn], t);
             t = warp_sum(t);
@@ -554,7 +557,7 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
                 // tvec was consumed by launch_apply_wy above and is refilled for the next step by k_hh_step_wy)
                 KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true, -1, W.T, W.tvec, W.ldt));
                 KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
-                k_hh_step_wy<<<1, 256, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
+                k_hh_step_wy<<<1, kHhStepThreads, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
                 c->stats.kernel_launches += 1;
                 PHhNewReflector f;
                 set_gate(f, c, true, j, 1);

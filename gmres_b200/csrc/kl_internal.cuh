@@ -291,6 +291,26 @@ struct FastDiv {
         const int ex = (int)((bits >> 52) & 0x7ff);
         ok = (man != 0x000fffffffffffffULL) && ex > 200 && ex < 1800;
     }
+    // two quotients with ONE warp-wide test for the rare operands (zero, tiny, huge, NaN): the common path is
+    // straight-line code instead of a divergence scaffold (BSSY / BRA / BSYNC) per division.  All 32 lanes of the
+    // warp must call it together.
+    __device__ __forceinline__ void div2(double x0, double x1, double &o0, double &o1) const {
+        const double a0 = x0 * rd, a1 = x1 * rd;
+        double r0 = fma(-a0, d, x0), r1 = fma(-a1, d, x1);
+        double q0 = fma(r0, rd, a0), q1 = fma(r1, rd, a1);
+        r0 = fma(-q0, d, x0);
+        r1 = fma(-q1, d, x1);
+        q0 = fma(r0, rd, q0);
+        q1 = fma(r1, rd, q1);
+        const double ax0 = fabs(x0), ax1 = fabs(x1);
+        const bool rare = !(ok && ax0 >= 0x1p-700 && ax0 <= 0x1p700 && ax1 >= 0x1p-700 && ax1 <= 0x1p700);
+        if (__any_sync(0xffffffffu, rare)) {
+            if (!(ok && ax0 >= 0x1p-700 && ax0 <= 0x1p700)) q0 = (x0 == 0.0 && ok) ? a0 : slow_div(x0, d);
+            if (!(ok && ax1 >= 0x1p-700 && ax1 <= 0x1p700)) q1 = (x1 == 0.0 && ok) ? a1 : slow_div(x1, d);
+        }
+        o0 = q0;
+        o1 = q1;
+    }
     __device__ __forceinline__ double div(double x) const {
         const double q0 = x * rd;
         double r = fma(-q0, d, x);
@@ -480,12 +500,16 @@ __device__ __forceinline__ double apply5_rt(int opk, double c, double l, double 
 struct Geo {
     int nx, ny, rows;
     int gy_main, rows_tail, main_end;
-    int h[4], p[4];
+    int h0, h1, h2, h3;       // staggered heights of a period (scalars, not arrays: a run-time index into a kernel
+    int p1, p2, p3;           // parameter makes the compiler copy the whole struct to local memory) ; prefix sums
 };
 __device__ __forceinline__ void tile_lines(const Geo &g, int by, int &j0, int &j1) {
     if (by < g.gy_main) {
-        j0 = (by >> 2) * (4 * g.rows) + g.p[by & 3];
-        j1 = min(j0 + g.h[by & 3], g.main_end);
+        const int k = by & 3;
+        const int pk = k == 0 ? 0 : (k == 1 ? g.p1 : (k == 2 ? g.p2 : g.p3));
+        const int hk = k == 0 ? g.h0 : (k == 1 ? g.h1 : (k == 2 ? g.h2 : g.h3));
+        j0 = (by >> 2) * (4 * g.rows) + pk;
+        j1 = min(j0 + hk, g.main_end);
     } else {
         j0 = g.main_end + (by - g.gy_main) * g.rows_tail;
         j1 = min(j0 + g.rows_tail, g.ny);
@@ -713,12 +737,16 @@ struct PwBase {
 
 
 // post functor launched on its own (multi-GPU: after the all-reduce)
-static __global__ void k_post(const PostAny post, const int *flags, const int step, const int run_on_conv) {
+// red / red_src: the post functors read S_RED[0]; a kernel that reduces several sums (the Chebyshev chains keep
+// both z.z and r.z so that their inner loop needs no selects) names the one to use
+static __global__ void k_post(const PostAny post, const int *flags, const int step, const int run_on_conv,
+                              double *red = nullptr, const int red_src = 0) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (flags) {   // same gate as the kernel whose sums it consumes
             const int ca = flags[I_CONV_AT];
             if (!(ca < 0 || (run_on_conv && ca == step))) return;
         }
+        if (red && red_src) red[0] = red[red_src];
         post.run();
     }
 }
@@ -750,10 +778,10 @@ inline int stencil_rows(int nx, int ny, int vec) {
 // all-reduce the local sums and run the post functor in its own kernel.
 template <class Post>
 inline int finish_reduction(Ctx *c, int nred, const Post &post, const int *flags = nullptr, int step = 0,
-                            int run_on_conv = 0) {
+                            int run_on_conv = 0, int red_src = 0) {
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, c->d_S + S_RED, nred));
-        k_post<<<1, 32, 0, c->stream>>>(to_any(post), flags, step, run_on_conv);
+        k_post<<<1, 32, 0, c->stream>>>(to_any(post), flags, step, run_on_conv, c->d_S + S_RED, red_src);
         c->stats.kernel_launches++;
     }
     return KL_OK;
@@ -820,7 +848,8 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     g->gy_main = (int)gy_main;
     g->rows_tail = (int)(gy_tail > 0 ? rt : rows);
     g->main_end = (int)main_end;
-    for (int k = 0; k < 4; ++k) { g->h[k] = (int)h[k]; g->p[k] = (int)p[k]; }
+    g->h0 = (int)h[0]; g->h1 = (int)h[1]; g->h2 = (int)h[2]; g->h3 = (int)h[3];
+    g->p1 = (int)p[1]; g->p2 = (int)p[2]; g->p3 = (int)p[3];
     *grid = dim3((unsigned)gx, (unsigned)(gy_main + gy_tail));
     return true;
 }

@@ -249,7 +249,7 @@ int pc_apply_any(Prob *P, const double *r, double *z, double *aux, double *aux2,
         f.z = dst; f.d_out = (kc == k) ? nullptr : aux2; f.mode = (kc == k) ? mode : 0; \
         f.theta = theta;                                                                \
         for (int s = 0; s < LL; ++s) { f.c1[s] = c1s[s]; f.c2[s] = c2s[s]; }            \
-        if (kc == k && mode != 0) { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, post)); } \
+        if (kc == k && mode != 0) { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, post, mode == 2 ? 1 : 0)); } \
         else { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, NoPost{})); }           \
     } break;
             switch (kc) {
@@ -277,7 +277,7 @@ int pc_apply_any(Prob *P, const double *r, double *z, double *aux, double *aux2,
         set_gate(f, c, gated);                                                          \
         f.z = z; f.mode = mode;                                                         \
         for (int s = 0; s < LL; ++s) { f.c1[s] = c1s[s]; f.c2[s] = c2s[s]; }            \
-        if (mode != 0) { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, post)); }     \
+        if (mode != 0) { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, post, mode == 2 ? 1 : 0)); } \
         else { KL_TRY(launch_chain(c, &P->op, f, P->nx, P->nyl, NoPost{})); }           \
     } break;
                 switch (kb) {

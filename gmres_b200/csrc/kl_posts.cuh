@@ -158,8 +158,10 @@ struct PostAny {
         PostLanAlpha v_PostLanAlpha;
         PostLanBeta v_PostLanBeta;
     } u;
-    // __noinline__: one copy per translation unit, and its registers do not count towards the kernels' budgets
-    __device__ __noinline__ void run() const {
+    // inlined into the reducing kernels' tails: a call would take the address of the kernel parameter and force a
+    // copy of the whole union to local memory (216 B of stack and 12-16 more registers per kernel when it was
+    // __noinline__); the switch is a few hundred bytes of code executed by one thread once per launch
+    __device__ __forceinline__ void run() const {
         switch (kind) {
             case PK_NoPost: u.v_NoPost.run(); break;
             case PK_PostStoreRed: u.v_PostStoreRed.run(); break;

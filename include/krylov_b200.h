@@ -107,6 +107,8 @@ int kl_version(void);
  * stream); NULL = the handle's own non-blocking stream.  In device-pointer mode the caller's vectors must be
  * ordered against the handle's stream: either share the stream that produces / consumes them, or synchronise. */
 int kl_set_stream(kl_handle_t h, void *cuda_stream);
+/* the stream the handle enqueues on (for event-based ordering against the caller's own streams) */
+int kl_get_stream(kl_handle_t h, void **cuda_stream);
 int kl_synchronize(kl_handle_t h);
 
 enum { KL_POINTER_HOST = 0, KL_POINTER_DEVICE = 1 };

@@ -214,3 +214,99 @@ def test_slab_chebyshev_chain_world2_matches_oracle(ko):
         zo = ko.apply_precond(ko.cheb_fn(k), ko.stvec_fn(), rg, (0.2, 8.2), ns)
         # numpy evaluates c1*d + c2*(...) with two roundings where the oracle and the CUDA kernel use one fma
         assert np.allclose(z, zo, rtol=1e-13, atol=1e-15), (k, np.abs(z - zo).max())
+
+
+# ---- "producer pushes" halo scheme of the fused multi-GPU CG (kl_cg.cu FCgDirX2 / FCgRUpdate, kCbPush slots) ------
+def _worker_push(rank, world, port, ns, out):
+    """Mirror of the multi-GPU plain-CG iteration of libkrylov_b200: the operator is applied twice per iteration
+    (A p is never stored), the x update is deferred by one iteration, and there is NO halo exchange step: the
+    kernel that produces p_new / r_new stores its first and last line into the neighbours' slot
+    [parity = iteration & 1][vector][direction]; consumers read parity (iteration - 1) & 1; the all-reduce that
+    ends each kernel is the only synchronisation."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gmres_b200.dist import slab_partition
+
+    nx = ns
+    j0, nyl = slab_partition(ns, rank, world)
+    slots = np.zeros((2, 2, 2, nx))        # [parity][0 = r, 1 = p][0 = lo (from rank-1), 1 = hi (from rank+1)]
+    R_, P_ = 0, 1
+
+    def push(par, vec, first, last):
+        """my first line -> rank-1's hi slot ; my last line -> rank+1's lo slot (comm_push_send / _recv)"""
+        reqs = []
+        t_lo, t_hi = torch.zeros(nx, dtype=torch.float64), torch.zeros(nx, dtype=torch.float64)
+        if rank > 0:
+            reqs += [dist.isend(torch.from_numpy(first.copy()), rank - 1), dist.irecv(t_lo, rank - 1)]
+        if rank < world - 1:
+            reqs += [dist.isend(torch.from_numpy(last.copy()), rank + 1), dist.irecv(t_hi, rank + 1)]
+        for q in reqs:
+            q.wait()
+        if rank > 0:
+            slots[par, vec, 0] = t_lo.numpy()
+        if rank < world - 1:
+            slots[par, vec, 1] = t_hi.numpy()
+
+    def apply_with_halo(U, lo, hi):
+        Pd = np.zeros((nyl + 2, nx + 2))
+        Pd[1:-1, 1:-1] = U
+        if rank > 0:
+            Pd[0, 1:-1] = lo
+        if rank < world - 1:
+            Pd[-1, 1:-1] = hi
+        s = ((Pd[1:-1, :-2] + Pd[1:-1, 2:]) + Pd[2:, 1:-1]) + Pd[:-2, 1:-1]
+        return 4.0 * U - s
+
+    ones = np.ones((nyl, nx))
+    push(0, R_, ones[0], ones[-1])
+    b = apply_with_halo(ones, slots[0, R_, 0], slots[0, R_, 1])        # b = A*1 on the slab
+    slots[:] = 0.0
+    r, p, x = b.copy(), np.zeros_like(b), np.zeros_like(b)
+    push(0, R_, r[0], r[-1])                                           # set-up push (comm_push_lines): r0 and p0 = 0
+    push(0, P_, p[0], p[-1])
+    rr = _allsum(float(np.sum(r * r)))                                 # ... ordered by this all-reduce
+    beta, alpha, hist, it_conv = 0.0, 0.0, [], -1
+    for it in range(1, 5000):
+        pin, pout = (it - 1) & 1, it & 1
+        # K1: x += alpha_prev p ; p' = r + beta p ; (A p').p' ; push p' lines
+        x += alpha * p
+        pn = r + beta * p
+        pn_lo = slots[pin, R_, 0] + beta * slots[pin, P_, 0]
+        pn_hi = slots[pin, R_, 1] + beta * slots[pin, P_, 1]
+        ap = apply_with_halo(pn, pn_lo, pn_hi)
+        push(pout, P_, pn[0], pn[-1])
+        alpha = rr / _allsum(float(np.sum(ap * pn)))
+        # K2: p' and A p' recomputed from the SAME (unchanged) halo lines ; r' = r - alpha A p' ; push r' lines
+        ap2 = apply_with_halo(r + beta * p, pn_lo, pn_hi)
+        assert np.array_equal(ap2, ap)
+        rnew = r - alpha * ap2
+        push(pout, R_, rnew[0], rnew[-1])
+        rn = _allsum(float(np.sum(rnew * rnew)))
+        beta, rr = rn / rr, rn
+        r, p = rnew, pn
+        hist.append(np.sqrt(rn))
+        if hist[-1] < 1e-9:
+            it_conv = it
+            break
+    x += alpha * p                                                     # flush of the deferred update
+    out[rank] = dict(j0=j0, nyl=nyl, b=b.reshape(-1), x=x.reshape(-1), it=it_conv, hist=np.array(hist))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pushed_halo_cg_matches_oracle(ko, world):
+    ns = 57
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_push, args=(world, _free_port(), ns, out), nprocs=world, join=True)
+    A = ko.stvec_fn()
+    b = ko.manufactured_rhs(A, ns)
+    o = ko.cg_omp(A, b, 1e-9, 5000)
+    parts = [out[r] for r in range(world)]
+    assert np.array_equal(np.concatenate([p["b"] for p in parts]), b)
+    assert all(p["it"] == o.iter for p in parts)
+    assert np.allclose(parts[0]["hist"], o.history, rtol=1e-7)
+    assert np.abs(np.concatenate([p["x"] for p in parts]) - o.x).max() < 1e-10
