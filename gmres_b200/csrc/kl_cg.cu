@@ -106,6 +106,7 @@ struct FCgDirX2 : StencilBase<2, 1> {
 struct FCgRUpdate : StencilBase<2, 1> {
     static constexpr bool kPush = true;
     static constexpr bool kLateWait = true;
+    static constexpr bool kReverse = true;     // starts on the lines of r and p that K1 read last (still in L2)
     double *r_new;
     const double *S;
     double *push_first, *push_last;   // neighbours' slots for r_new's first / last line

@@ -249,6 +249,43 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
 }
 
 
+// ---- one Arnoldi step's operator part in ONE pass (temporally blocked, kl_chain_tma.cuh) -----------------------
+//   V_j = w / h ; z = A V_j ; w' = cbpr2(z) = z/d + alpha (z - A (z/d))     gmres_mgsr.f90:384,336,337 ; chebyshev.f90:27-37
+// reads w, writes V_j and w': 24n B and one launch instead of 24n + 16n B and two (FScaleApply, FCbpr2).  Same
+// arithmetic per point as those two kernels (same divisions, same fma), so the results are bit-identical.
+struct ChGmresStep : ChainBase<1, 2, 1, 0> {
+    double *v_out, *w_out;
+    const double *S;
+    int s_idx;
+    double d, calpha;
+    FastDiv fh, fd;
+    __device__ __forceinline__ void init() {
+        fh.set(S[s_idx]);
+        fd.set(d);
+    }
+    __device__ __forceinline__ void level0(bool out, size_t idx, const double (&raw)[1][2], double (&u)[2],
+                                           double (&cc)[1][2], double *) const {
+        fh.div2(raw[0][0], raw[0][1], u[0], u[1]);                                   // :384
+        cc[0][0] = cc[0][1] = 0.0;
+        if (out) stg2(v_out + idx, u[0], u[1]);
+    }
+    template <class RAW>
+    __device__ __forceinline__ void level(int lv, bool out, size_t idx, const double (&up)[2], const double (&au)[2],
+                                          const double (&cin)[1][2], RAW, const double (&)[1][2], double (&u)[2],
+                                          double (&cout)[1][2], double *) const {
+        if (lv == 1) {
+            fd.div2(au[0], au[1], u[0], u[1]);                                       // chebyshev.f90:28-30  z0 = r/d, r = A V_j
+            cout[0][0] = au[0];
+            cout[0][1] = au[1];
+        } else {
+            u[0] = fma(calpha, cin[0][0] - au[0], up[0]);                            // :34-36
+            u[1] = fma(calpha, cin[0][1] - au[1], up[1]);
+            cout[0][0] = cout[0][1] = 0.0;
+            if (out) stg2(w_out + idx, u[0], u[1]);
+        }
+    }
+};
+
 // ---- back substitution by one warp (gmres_mgsr.f90:394-398) -------------------
 // lane 0 runs the reference's sequential recurrence; the warp stages row i of H.
 __global__ void k_backsolve(const GmresDev G) {
@@ -468,13 +505,14 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     KL_CUDA(c, cudaEventRecord(evA, c->stream));
 
     const bool dev = c->pointer_mode == KL_POINTER_DEVICE;
-    size_t need = ws_need(ldv * (size_t)(m + 1)) + 6 * ws_need(n) + ws_need((size_t)ldh * m) +
+    size_t need = ws_need(ldv * (size_t)(m + 1)) + 7 * ws_need(n) + ws_need((size_t)ldh * m) +
                   10 * ws_need(m + 2) + ws_need((size_t)(m + 2) * (m + 2));
     KL_TRY(ws_reserve(c, need));
     ws_reset(c);
     double *V = ws_take<double>(c, ldv * (size_t)(m + 1));
     double *w = ws_take<double>(c, n), *z = ws_take<double>(c, n), *aux = ws_take<double>(c, n);
     double *aux2 = ws_take<double>(c, n);
+    double *w2 = ws_take<double>(c, n);     // second w buffer of the one-pass step (its input and output differ)
     double *db = dev ? const_cast<double *>(b) : ws_take<double>(c, n);
     double *dx = dev ? x : ws_take<double>(c, n);
     GmresDev G;
@@ -513,12 +551,16 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     int status = KL_NOT_CONVERGED, n_out = 0, restart_out = max_restarts, cycles = 0;
     double bytes = 0.0;
     double *const w_base = w, *const z_base = z;
+    // V_j = w/h, z = A V_j and w = cbpr2(z) as one temporally blocked pass (same decision on every rank)
+    const bool chain_step = fused && P.pc.kind == KL_PC_CBPR2 && chain_ok(&P, 2);
+    const Cbpr2Coef cbc = chain_step ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
     // One restart cycle = a fixed sequence of launches (every pointer, column count and step index is known on
     // the host; convergence is a device-side gate), so it can be captured once and replayed as a CUDA graph:
     // at 300^2 (BASELINE config 1) a cycle is ~480 launches of 5-20 us kernels and launch overhead dominates.
     auto enqueue_cycle = [&]() -> int {
         w = w_base;
         z = z_base;
+        double *wn = w2;
         // g = 0 ; H = 0 (:312).  (V = 0 is not needed: every column is written before it is read.)
         KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
         KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
@@ -541,7 +583,18 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
             double *Vj = V + (size_t)j * ldv;
             // V_j = w / norm ; z = A V_j   (:325-329 / :384 of the previous step ; :336).
             // omp: V_j is also written when the previous step converged (:384 precedes :385).
-            if (fused) {
+            if (chain_step) {
+                ProfScope ps(c, 0, "gmres_scale_apply_precond (chain: V_j=w/h; z=A V_j; w=cbpr2(z))", 24.0 * n);
+                Halo H;
+                const double *vecs[1] = {w};
+                KL_TRY(halo_exchange_lines(&P, vecs, 1, 2, &H));
+                ChGmresStep f;
+                set_io(f, &P, vecs, H);
+                set_gate(f, c, true, j - 1, mf ? 0 : 1);
+                f.v_out = Vj; f.w_out = wn; f.S = c->d_S; f.s_idx = norm_idx; f.d = cbc.d; f.calpha = cbc.alpha;
+                KL_TRY(launch_chain(c, &P.op, f, P.nx, P.nyl, NoPost{}));
+                std::swap(w, wn);
+            } else if (fused) {
                 ProfScope ps(c, 0, "gmres_scale_apply (stencil: V_j=w/h; z=A V_j)", 24.0 * n);
                 Halo H;
                 const double *vecs[1] = {w};
@@ -559,7 +612,9 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
                 KL_TRY(op_apply(&P, Vj, z, true));
             }
             // w = M^-1 z (:337)
-            if (prec) {
+            if (chain_step) {
+                // done above
+            } else if (prec) {
                 ProfScope ps(c, 1, "gmres_precond (stencil: w=M^-1 z)", 16.0 * n);
                 KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
             } else std::swap(w, z);
@@ -618,7 +673,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
                 bytes += (32.0 * ncols + 48.0) * n;
                 }
             }
-            bytes += (24.0 + (prec ? 16.0 : 0.0)) * n;
+            bytes += (24.0 + ((prec && !chain_step) ? 16.0 : 0.0)) * n;
             norm_idx = S_HVAL;
         }
         // V_{m+1} = w / h_val (:384).  omp: also on the converged step ; mf: not (:172-176)

@@ -137,7 +137,8 @@ struct kl_context_s {
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
-    int opt_stencil_stagger = 1; // staggered tile heights (KL_OPT_STENCIL_STAGGER)
+    int opt_reverse = 1;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE)
+    int opt_stencil_stagger = 0; // staggered tile heights (KL_OPT_STENCIL_STAGGER): measured neutral, off by default
     int opt_stencil_tail = -1;  // lines per CTA in the tapered tail (-1 auto, 0 off), KL_OPT_STENCIL_TAIL
     int opt_pdl = 1;            // programmatic dependent launch between the fused CG kernels (KL_OPT_PDL)
     // comm
@@ -502,7 +503,12 @@ struct Geo {
     int gy_main, rows_tail, main_end;
     int h0, h1, h2, h3;       // staggered heights of a period (scalars, not arrays: a run-time index into a kernel
     int p1, p2, p3;           // parameter makes the compiler copy the whole struct to local memory) ; prefix sums
+    int reverse;              // 1: the tiling is mirrored, so the CTAs scheduled FIRST work on the LAST lines
 };
+// `reverse`: consecutive kernels of an iteration stream the same vectors (CG: K1 reads r, p ; K2 reads r, p again ;
+// the next K1 reads the r that K2 wrote).  When a kernel starts where its predecessor stopped, the lines the
+// predecessor touched last are still in the 126 MB L2 -- on the 268 MB-per-vector slabs of the 8-GPU strong-scaling
+// run that is a tenth of the traffic; on 2 GB vectors it is noise.
 __device__ __forceinline__ void tile_lines(const Geo &g, int by, int &j0, int &j1) {
     if (by < g.gy_main) {
         const int k = by & 3;
@@ -513,6 +519,11 @@ __device__ __forceinline__ void tile_lines(const Geo &g, int by, int &j0, int &j
     } else {
         j0 = g.main_end + (by - g.gy_main) * g.rows_tail;
         j1 = min(j0 + g.rows_tail, g.ny);
+    }
+    if (g.reverse) {
+        const int t = j0;
+        j0 = g.ny - j1;
+        j1 = g.ny - t;
     }
 }
 
@@ -528,6 +539,8 @@ struct StencilBase {
     // the whole prologue -- barrier setup, the first TMA stages, the first lines of u -- overlaps the
     // predecessor's tail; late_init() then reads the predecessor's scalars.
     static constexpr bool kLateWait = false;
+    // kReverse: march the grid from its last lines to its first (see Geo::reverse)
+    static constexpr bool kReverse = false;
     __device__ __forceinline__ void late_init() {}
     const double *in[NIN_];
     const double *lo[NIN_];
@@ -695,8 +708,10 @@ k_stencil(const F f_in, const Geo g, const RedCtl rc, const PostAny post, const 
 // ------------------------------------------------------------------------
 constexpr int kPwThreads = 256;
 
+// (min 3 resident blocks per SM = at most 85 registers: PBiUpdate reached 108 once the run-time post dispatch and
+// the parallel final reduction were inlined into its tail, i.e. 2 blocks per SM, and lost a quarter of its bandwidth)
 template <class F, int VEC>
-__global__ void __launch_bounds__(kPwThreads)
+__global__ void __launch_bounds__(kPwThreads, 3)
 k_pointwise(const F f_in, const size_t n, const RedCtl rc, const PostAny post, const int fuse_post) {
     griddep_wait();
     if (f_in.skip()) return;
@@ -806,8 +821,8 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     const long want = (long)kNumSM * (gx >= 32 ? 28 : 8);
     long rows = ((long)ny * gx + want - 1) / want;
     if (rows < 8) rows = 8;
-    if (rows > 64) rows = 64;
-    if (rows_opt > 0) rows = rows_opt;     // KL_OPT_STENCIL_ROWS (tuning experiments)
+    if (rows > 128) rows = 128;            // 16384^2 on one GPU: 128-line tiles with a 32-line tail measured 2 % faster
+    if (rows_opt > 0) rows = rows_opt;     // than 64 / 16 (scripts/slab_sweep2.py) ; KL_OPT_STENCIL_ROWS overrides
     if (rows > ny) rows = ny;
     long gy = (ny + rows - 1) / rows;
     // tapered tail (KL_OPT_STENCIL_TAIL: -1 auto, 0 off, > 0 lines per tail CTA): the last half wave of CTAs gets
@@ -863,6 +878,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     const int strip = tma ? kTmaStrip : kStencilThreads * vec;
     Geo g{};
     g.nx = nx; g.ny = ny;
+    const int reverse = (F::kReverse && c->opt_reverse) ? 1 : 0;
     dim3 grid;
     f.coef = OpCoef{op->eps_x, op->eps_y, 2.0 * (op->eps_x + op->eps_y)};
     RedCtl rc = redctl(c);
@@ -898,6 +914,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
         }                                                                                           \
         if (!stencil_geometry(nx, ny, strip, (long)oc * kNumSM, &g, &grid, c->opt_stencil_rows, c->opt_stencil_tail, c->opt_stencil_stagger)) \
             return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");           \
+        g.reverse = reverse;                                                                        \
         cfg.gridDim = grid;                                                                         \
         cfg.dynamicSmemBytes = SMEM;                                                                \
     }

@@ -136,8 +136,11 @@ enum {
                                  the prologue of one overlaps the tail of the other; 0: plain stream order      */
     KL_OPT_STENCIL_TAIL = 17, /* lines per CTA in the tapered tail of the stencil kernels' grids: -1 (default) = a quarter
                                  of the regular tile height, 0 = off                                            */
-    KL_OPT_STENCIL_STAGGER = 18, /* 1 (default): CTA heights of the stencil kernels staggered (5/8 .. 11/8 of the mean) so
-                                 that CTAs do not start and drain in lockstep waves; 0: equal heights              */
+    KL_OPT_STENCIL_STAGGER = 18, /* 1: CTA heights of the stencil kernels staggered (5/8 .. 11/8 of the mean) so that CTAs
+                                 do not start and drain in lockstep waves; 0 (default): equal heights -- measured
+                                 neutral on B200 (profiles/r02_cta_timeline.md)                                   */
+    KL_OPT_REVERSE = 19,      /* 1 (default): the second kernel of a CG iteration marches the grid from its last lines to
+                                 its first, i.e. starts on what the first kernel left in L2 (tuning only)          */
     KL_OPT_PUSH_HALO = 16,    /* multi-GPU with peer memory: 1 (default) = the kernel that PRODUCES a vector pushes its
                                  boundary lines into the neighbours' halo slots (no halo kernel; the all-reduce that
                                  ends the kernel is the barrier); 0 = separate halo push before every operator apply */

@@ -129,3 +129,26 @@ def test_cg_operator_twice_matches_stored_ap(kl, h, nx, ny):
     assert g.status == 0 and abs(g.iter - s.iter) <= 1
     assert g.stats["algorithmic_bytes"] / g.iter / (nx * ny) == pytest.approx(64.0)
     assert np.abs(g.x - 1).max() < 1e-7 and np.abs(g.x - s.x).max() < 1e-9
+
+
+@pytest.mark.parametrize("nx,ny,m", [(96, 96, 30), (300, 300, 95), (130, 77, 20), (1024, 256, 24)])
+def test_gmres_one_pass_step_bit_identical_to_two_kernels(kl, h, nx, ny, m):
+    """GMRES-MGSR + cbpr2: V_j = w/h, z = A V_j and w = cbpr2(z) as ONE temporally blocked pass (ChGmresStep,
+    kl_gmres.cu) against the two separate kernels (KL_OPT_CHAIN = 0).  Every point sees the same divisions and the
+    same fma, the orthogonalisation kernels are the same ones: the residual history, H and x are bit-identical.
+    Both with and without CUDA-graph replay of the restart cycle."""
+    P = (8.2, 0.2)
+    for op in (kl.stvec, kl.aniso(1.0, 0.05)):
+        b = h.apply(op, np.ones(nx * ny), nx, ny)
+        run = lambda: h.gmres_mgsr_omp(op, b, m, 1e-9, kl.cbpr2, P, nx=nx, ny=ny)
+        g = run()
+        u = _no_chain(kl, h, run)
+        assert g.status == 0 and (g.n_out, g.restart_out) == (u.n_out, u.restart_out)
+        assert np.array_equal(g.history, u.history) and np.array_equal(g.x, u.x)
+        assert np.array_equal(g.final_err, u.final_err)
+        h.set_option(5, 0)          # KL_OPT_USE_GRAPH off: eager launches
+        try:
+            e = run()
+        finally:
+            h.set_option(5, 1)
+        assert np.array_equal(e.history, g.history) and np.array_equal(e.x, g.x)
