@@ -13,7 +13,7 @@ configs[1] (Householder GMRES(95), 1024^2) and configs[4] (BiCGSTAB, 8192^2/GPU)
 Bytes: `roofline` and `roofline_iter` use the bytes the kernels actually have to move (kl_get_stats /
 kl_get_profile, listed per kernel in DESIGN.md section 3): plain CG executes 64n B per iteration (the operator
 is applied twice instead of storing A p; SURVEY.md section 8d assumed 80n), PCG + cbpr2 80n, BiCGSTAB + cbpr2
-160n.  `roofline.traffic` is the DRAM traffic ncu measured for the dominant kernel (profiles/r01_traffic.json).
+160n.  `roofline.traffic` is the DRAM traffic ncu measured for the dominant kernel (profiles/r02_traffic.json).
 
 Inputs are synthetic and deterministic (x_true = 1, b = A*1; no RNG), resident in HBM
 before the timed region; vectors (2.1 GB each) are far larger than the 126 MB L2, so no
@@ -278,7 +278,10 @@ def gpu_arm(args):
             if dom:
                 traffic, tsrc = None, None
                 try:
-                    with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as tf:
+                    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+                    if not os.path.exists(tpath):
+                        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+                    with open(tpath) as tf:
                         tj = json.load(tf)
                     key = dom["name"].split(" ")[0]
                     ent = tj["bytes_per_unknown"].get(key)

@@ -499,6 +499,9 @@ int kl_create(kl_handle_t *h, int device) {
     if (const char *e = getenv("KL_STENCIL_TAIL")) c->opt_stencil_tail = atoi(e);
     if (const char *e = getenv("KL_STENCIL_STAGGER")) c->opt_stencil_stagger = atoi(e) != 0;
     if (const char *e = getenv("KL_REVERSE")) c->opt_reverse = atoi(e) != 0;
+    if (const char *e = getenv("KL_COOP")) c->opt_coop = atoi(e) != 0;
+    if (const char *e = getenv("KL_PERSISTENT")) c->opt_persistent = atoi(e) != 0;
+    if (const char *e = getenv("KL_PERSIST_OCC")) c->opt_persist_occ = atoi(e);
     if (const char *e = getenv("KL_STENCIL_ROWS")) c->opt_stencil_rows = atoi(e);
     if (const char *e = getenv("KL_PUSH_HALO")) c->opt_push_halo = atoi(e) != 0;
     if (const char *e = getenv("KL_INLINE_ALLREDUCE")) c->opt_inline_ar = atoi(e) != 0;
@@ -635,6 +638,8 @@ int kl_set_option(kl_handle_t h, int key, int value) {
         case KL_OPT_STENCIL_TAIL: h->opt_stencil_tail = value; break;
         case KL_OPT_STENCIL_STAGGER: h->opt_stencil_stagger = value != 0; break;
         case KL_OPT_REVERSE: h->opt_reverse = value != 0; break;
+        case KL_OPT_COOP: h->opt_coop = value != 0; break;
+        case KL_OPT_PERSISTENT: h->opt_persistent = value != 0; break;
         case KL_OPT_PUSH_HALO: h->opt_push_halo = value != 0; break;
         default: return KL_ERR_INVALID;
     }
@@ -662,6 +667,8 @@ int kl_get_option(kl_handle_t h, int key, int *value) {
         case KL_OPT_STENCIL_TAIL: *value = h->opt_stencil_tail; break;
         case KL_OPT_STENCIL_STAGGER: *value = h->opt_stencil_stagger; break;
         case KL_OPT_REVERSE: *value = h->opt_reverse; break;
+        case KL_OPT_COOP: *value = h->opt_coop; break;
+        case KL_OPT_PERSISTENT: *value = h->opt_persistent; break;
         case KL_OPT_PUSH_HALO: *value = h->opt_push_halo; break;
         default: return KL_ERR_INVALID;
     }

@@ -24,6 +24,8 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "kl_gmres.cuh"
 #include "kl_tallskinny_tma.cuh"
 
@@ -176,16 +178,12 @@ k_vtw(const double *__restrict__ V, const size_t ldv, const double *__restrict__
 }
 
 // ---- w_out = w - V(:,0..ncols-1) h  (+ ||w_out||^2, + Givens in the last block) --
-// FMA order = column order (the CPU twin's CGS2 loop).
+// FMA order = column order (the CPU twin's CGS2 loop).  wmvh_pass is the body (whole grid); k_wmvh the kernel.
 template <int VEC>
-__global__ void __launch_bounds__(kTsThreads)
-k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n, const int ncols,
-       const double *__restrict__ h, const RedCtl rc, const int want_norm, const GmresDev G,
-       const int j, const int fuse_givens, const int *__restrict__ flags) {
-    // want_norm: bit 0 = reduce ||w||^2 ; bit 1 = selective mode: do nothing when I_SKIP3 is set
-    if (flags && flags[I_CONV_AT] >= 0) return;
-    if ((want_norm & 2) && flags[I_SKIP3]) return;
-    extern __shared__ double sm[];   // max(ncols, 3*(m+2)) doubles + reduction scratch
+__device__ __forceinline__ void wmvh_pass(const double *__restrict__ V, const size_t ldv, double *w, const size_t n,
+                                          const int ncols, const double *__restrict__ h, const RedCtl &rc,
+                                          const int want_norm, const GmresDev &G, const int j, const int fuse_givens,
+                                          double *sm /* max(ncols, 3*(m+2)) doubles */) {
     double *sh = sm;
     for (int c = threadIdx.x; c < ncols; c += kTsThreads) sh[c] = h[c];
     __syncthreads();
@@ -248,6 +246,38 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
     }
 }
 
+template <int VEC>
+__global__ void __launch_bounds__(kTsThreads)
+k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n, const int ncols,
+       const double *__restrict__ h, const RedCtl rc, const int want_norm, const GmresDev G,
+       const int j, const int fuse_givens, const int *__restrict__ flags) {
+    // want_norm: bit 0 = reduce ||w||^2 ; bit 1 = selective mode: do nothing when I_SKIP3 is set
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    if ((want_norm & 2) && flags[I_SKIP3]) return;
+    extern __shared__ double sm[];   // max(ncols, 3*(m+2)) doubles + reduction scratch
+    wmvh_pass<VEC>(V, ldv, w, n, ncols, h, rc, want_norm, G, j, fuse_givens, sm);
+}
+
+// ---- the whole CGS2 orthogonalisation of one Arnoldi step as ONE cooperative kernel (single GPU, small grids) ----
+//   h1 = V^T w ; H(:,j) = h1      | grid barrier |  w -= V h1 ; h2 = V^T w ; H(:,j) += h2   | grid barrier |
+//   w -= V h2 ; ||w|| ; Givens, residual estimate, convergence flag (last block)
+// At 300^2 (BASELINE config 1, the reference's own headline problem) V is L2-resident and each of the three passes is
+// a 15-20 us kernel whose time is launch, ramp and reduction tail, not data; as three phases of one persistent
+// kernel they cost one launch and two ~2 us barriers.  Same device code, same partial-sum order => same bits.
+__global__ void __launch_bounds__(kTsThreads, 2)
+k_cgs2_coop(const __grid_constant__ CUtensorMap tmV, const double *__restrict__ V, const size_t ldv, double *w,
+            const size_t n, const int nc, const int RM, double *__restrict__ partials, unsigned int *counter,
+            const RedCtl rc, const GmresDev G, const int j, const int *__restrict__ flags) {
+    if (flags && flags[I_CONV_AT] >= 0) return;          // grid-uniform: every CTA leaves before the first barrier
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const TsTail none{nullptr, nullptr, 0};
+    ts_pass<false>(tmV, w, n, nc, RM, nullptr, partials, counter, G.hvec, G, j, 1, -1, none, smem_raw);
+    grid.sync();
+    ts_pass<true>(tmV, w, n, nc, RM, G.hvec, partials, counter, G.hvec2, G, j, 2, -1, none, smem_raw);
+    grid.sync();
+    wmvh_pass<2>(V, ldv, w, n, nc, G.hvec2, rc, 1, G, j, 1, reinterpret_cast<double *>(smem_raw));
+}
 
 // ---- one Arnoldi step's operator part in ONE pass (temporally blocked, kl_chain_tma.cuh) -----------------------
 //   V_j = w / h ; z = A V_j ; w' = cbpr2(z) = z/d + alpha (z - A (z/d))     gmres_mgsr.f90:384,336,337 ; chebyshev.f90:27-37
@@ -443,6 +473,48 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     return KL_OK;
 }
 
+// cooperative CGS2 step (see k_cgs2_coop): single GPU, TMA path, problems small enough to be launch-bound
+bool cgs2_coop_ok(Ctx *c, size_t n, size_t ldv, int m) {
+    return c->nranks == 1 && c->opt_coop && !c->opt_profile && c->opt_ortho == KL_ORTHO_CGS2 &&
+           ts_tma_ok(c, n, ldv, m + 1) && n <= ((size_t)1 << 21);
+}
+int launch_cgs2_coop(Ctx *c, const double *V, size_t ldv, int ncols_total, double *w, size_t n, int nc,
+                     const GmresDev &G, int j) {
+    CUtensorMap tm;
+    KL_TRY(tmap_encode_v(c, &tm, V, n, ldv, ncols_total, nc));
+    const size_t smem = std::max(ts_tma_smem(nc), sizeof(double) * (size_t)std::max(nc + 8, 3 * (G.m + 2)) + 256);
+    static bool attr_done[kMaxDevices] = {};
+    if (!attr_done[c->device % kMaxDevices]) {
+        cudaFuncSetAttribute(k_cgs2_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        attr_done[c->device % kMaxDevices] = true;
+    }
+    int RM = ts_rm(nc);
+    const size_t ntiles = (n + (size_t)kTsRB * RM - 1) / ((size_t)kTsRB * RM);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cgs2_coop, kTsThreads, smem) != cudaSuccess || occ < 1)
+        return c->fail(KL_ERR_CUDA, "k_cgs2_coop occupancy");
+    int grid = (int)std::min<size_t>(ntiles, (size_t)kNumSM * std::min(occ, 2));
+    RedCtl rc = redctl(c);
+    const int *fl = c->d_I;
+    const double *Vc = V;
+    size_t ldv_ = ldv, n_ = n;
+    unsigned int *counter = c->d_counter + 1;
+    double *partials = c->d_partials;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_cgs2_coop, tm, Vc, ldv_, w, n_, nc, RM, partials, counter, rc, G, j, fl));
+    c->stats.kernel_launches++;
+    return KL_OK;
+}
+
 int launch_wmvh(Ctx *c, const double *V, size_t ldv, double *w, size_t n, int ncols, const double *h,
                 bool want_norm, const GmresDev &G, int j, bool givens, bool gated, bool honor_skip = false) {
     const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
@@ -554,6 +626,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     // V_j = w/h, z = A V_j and w = cbpr2(z) as one temporally blocked pass (same decision on every rank)
     const bool chain_step = fused && P.pc.kind == KL_PC_CBPR2 && chain_ok(&P, 2);
     const Cbpr2Coef cbc = chain_step ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
+    const bool coop = cgs2_coop_ok(c, n, ldv, m);
     // One restart cycle = a fixed sequence of launches (every pointer, column count and step index is known on
     // the host; convergence is a device-side gate), so it can be captured once and replayed as a CUDA graph:
     // at 300^2 (BASELINE config 1) a cycle is ~480 launches of 5-20 us kernels and launch overhead dominates.
@@ -652,6 +725,9 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
                     { ProfScope ps(c, 3, "gmres_wmvh (w-=V h update [+norm+Givens])", (8.0 * ncols + 16.0) * n);
                       KL_TRY(launch_wmvh(c, V, ldv, wj, n, ncols, G.hvec2, true, G, j, true, true, true)); }
                     bytes += (24.0 * ncols + 40.0) * n;
+                } else if (coop) {
+                    KL_TRY(launch_cgs2_coop(c, V, ldv, m + 1, wj, n, ncols, G, j));
+                    bytes += (24.0 * ncols + 40.0) * n;
                 } else if (ts_tma_ok(c, n, ldv, ncols, P.nx, P.ny)) {
                     // 3 passes over V: project ; update + project (fused, V tile staged once) ; update + norm
                     { ProfScope ps(c, 2, "gmres_vtw_tma (h1=V^T w, TMA-staged tall-skinny projection)", (8.0 * ncols + 8.0) * n);
@@ -696,7 +772,7 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
         gk.add('G').add(nx).add(ny).add(m).add(mf).add(P.op.kind).add(P.op.eps_x).add(P.op.eps_y).add(P.pc.kind)
             .add(P.pc.degree).add(P.params).add(c->opt_ortho).add(c->opt_reorth_eta_permille).add(c->opt_tma)
             .add(c->opt_chain).add(c->opt_stencil_rows).add(c->opt_stencil_tail).add(c->opt_stencil_stagger)
-            .add(c->opt_pdl).add(c->ws).add(db).add(dx).add(V).add(G.H);
+            .add(c->opt_pdl).add(c->opt_coop).add(c->ws).add(db).add(dx).add(V).add(G.H);
     }
     for (int st = 1; st <= max_restarts; ++st) {
         ++cycles;

@@ -137,6 +137,9 @@ struct kl_context_s {
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
+    int opt_persistent = 1;      // persistent CTAs in the TMA stencil kernels (KL_OPT_PERSISTENT)
+    int opt_persist_occ = 0;     // CTAs per SM of the persistent grid (0 = full occupancy)
+    int opt_coop = 1;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP)
     int opt_reverse = 1;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE)
     int opt_stencil_stagger = 0; // staggered tile heights (KL_OPT_STENCIL_STAGGER): measured neutral, off by default
     int opt_stencil_tail = -1;  // lines per CTA in the tapered tail (-1 auto, 0 off), KL_OPT_STENCIL_TAIL
@@ -504,6 +507,7 @@ struct Geo {
     int h0, h1, h2, h3;       // staggered heights of a period (scalars, not arrays: a run-time index into a kernel
     int p1, p2, p3;           // parameter makes the compiler copy the whole struct to local memory) ; prefix sums
     int reverse;              // 1: the tiling is mirrored, so the CTAs scheduled FIRST work on the LAST lines
+    int gx, gy;               // strips x line bands = tiles (the TMA kernel's persistent CTAs loop over them)
 };
 // `reverse`: consecutive kernels of an iteration stream the same vectors (CG: K1 reads r, p ; K2 reads r, p again ;
 // the next K1 reads the r that K2 wrote).  When a kernel starts where its predecessor stopped, the lines the
@@ -810,8 +814,10 @@ namespace kl {
 // the tail of a partially filled last wave is self-correcting (the remaining CTAs get the whole HBM
 // bandwidth), while few long CTAs load-balance badly: a "whole waves" geometry measured 8 % slower on the
 // 8-GPU strong-scaling case (2048 local lines), so the simple rule stays.  `resident` is unused for now.
+// persistent: the caller launches min(tiles, resident) CTAs that loop over the tiles, so the number of tiles is not
+// bounded by the reduction buffer (one partial per CTA)
 inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, dim3 *grid, int rows_opt = 0,
-                             int tail_opt = -1, int stagger = 1) {
+                             int tail_opt = -1, int stagger = 1, bool persistent = false) {
     const long gx = (nx + strip - 1) / strip;
     if (gx > kMaxBlocks) return false;
     // Wide grids (>= 32 strips): ~28 CTAs per SM.  A CTA lives ~100 us there, and the kernel ends with a ragged
@@ -850,7 +856,7 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     long main_end = ny - tail_lines;
     long gy_main = count_main(main_end);
     if (tail_lines > 0) gy_tail = (tail_lines + rt - 1) / rt;
-    if (gx * (gy_main + gy_tail) > kMaxBlocks) {   // the deterministic reduction keeps one partial per CTA
+    if (!persistent && gx * (gy_main + gy_tail) > kMaxBlocks) {   // the deterministic reduction keeps one partial per CTA
         const long max_gy = kMaxBlocks / gx;
         rows = (ny + max_gy - 1) / max_gy;
         for (int k = 0; k < 4; ++k) { h[k] = rows; p[k] = k * rows; }
@@ -863,6 +869,8 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     g->gy_main = (int)gy_main;
     g->rows_tail = (int)(gy_tail > 0 ? rt : rows);
     g->main_end = (int)main_end;
+    g->gx = (int)gx;
+    g->gy = (int)(gy_main + gy_tail);
     g->h0 = (int)h[0]; g->h1 = (int)h[1]; g->h2 = (int)h[2]; g->h3 = (int)h[3];
     g->p1 = (int)p[1]; g->p2 = (int)p[2]; g->p3 = (int)p[3];
     *grid = dim3((unsigned)gx, (unsigned)(gy_main + gy_tail));
@@ -901,7 +909,8 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     cfg.numAttrs = (pdl && c->opt_pdl) ? 1 : 0;
     // the opt-in for > 48 KB of dynamic shared memory and the occupancy are per device (a process may hold
     // handles on several devices)
-#define KL_ST_GEO(KERNEL, SMEM)                                                                     \
+#define KL_ST_GEO(KERNEL, SMEM) KL_ST_GEO2(KERNEL, SMEM, false)
+#define KL_ST_GEO2(KERNEL, SMEM, PERSIST)                                                           \
     {                                                                                               \
         static int occ[kMaxDevices] = {};                                                           \
         int &oc = occ[c->device % kMaxDevices];                                                     \
@@ -912,9 +921,16 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
                 oc < 1)                                                                             \
                 oc = 4;                                                                             \
         }                                                                                           \
-        if (!stencil_geometry(nx, ny, strip, (long)oc * kNumSM, &g, &grid, c->opt_stencil_rows, c->opt_stencil_tail, c->opt_stencil_stagger)) \
+        if (!stencil_geometry(nx, ny, strip, (long)oc * kNumSM, &g, &grid, c->opt_stencil_rows, c->opt_stencil_tail, c->opt_stencil_stagger, PERSIST)) \
             return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");           \
         g.reverse = reverse;                                                                        \
+        if (PERSIST) {   /* persistent CTAs: as many as are resident at once (KL_OPT_PERSIST_OCC CTAs per SM) */ \
+            long res = (long)((c->opt_persist_occ > 0 && c->opt_persist_occ < oc) ? c->opt_persist_occ : oc) * kNumSM; \
+            long tiles = (long)grid.x * grid.y;                                                     \
+            if (!c->opt_persistent) res = tiles;                                                    \
+            if (res > kMaxBlocks) res = kMaxBlocks;                                                 \
+            grid = dim3((unsigned)(tiles < res ? tiles : res));                                     \
+        }                                                                                           \
         cfg.gridDim = grid;                                                                         \
         cfg.dynamicSmemBytes = SMEM;                                                                \
     }
@@ -924,7 +940,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     // a run-time argument
 #define KL_ST_TMA(OPK)                                                                              \
     {                                                                                               \
-        KL_ST_GEO((k_stencil_tma<F, OPK>), smem)                                                    \
+        KL_ST_GEO2((k_stencil_tma<F, OPK>), smem, true)                                             \
         KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_stencil_tma<F, OPK>, f, g, rc, pa, fuse, tm));        \
     }
     if (tma) {
@@ -940,6 +956,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     }
 #undef KL_ST_TMA
 #undef KL_ST_GEO
+#undef KL_ST_GEO2
     c->stats.kernel_launches++;
     if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;

@@ -109,17 +109,16 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, co
     double *sbuf = reinterpret_cast<double *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NST * kStageBytes);
 
+    // PERSISTENT CTAs: the grid holds at most as many CTAs as are resident at once (launch_stencil); CTA c processes
+    // the tiles c, c + gridDim.x, c + 2 gridDim.x, ... (tile = strip + gx * line band, strips fastest).  The TMA ring
+    // runs ACROSS tile boundaries: while the last stages of one tile are consumed, the first stages of the next one
+    // are already in flight.  With one CTA per tile the 4-5 "waves" of a slab of the 8-GPU strong-scaling run each
+    // started and drained in lockstep, and every wave boundary was a few microseconds of idle memory system
+    // (profiles/r02_cta_timeline_k1.txt).
     const int tid = threadIdx.x, lane = tid & 31;
-    const int i0 = blockIdx.x * kTmaStrip;       // first output column of the strip
-    const int gi = i0 - 2 + 2 * tid;             // global column of this thread's pair
-    const bool outp = tid >= 1 && tid <= kStencilThreads - 2 && gi < g.nx;
     const bool has_l = lane == 0 && tid > 0;
     const bool has_r = lane == 31 && tid < kStencilThreads - 1;
-    int j0, j1;
-    tile_lines(g, blockIdx.y, j0, j1);
-    const int jstart = j0 - 1;
-    const int nrows = j1 - j0 + 2;
-    const int nst = (nrows + SR - 1) / SR;
+    const int ntiles = g.gx * g.gy;
 
     if (tid == 0) {
 #pragma unroll
@@ -127,21 +126,52 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int k) {
-        const int s = k % NST;
+    // producer state (used by thread 0 only): the next stage to issue is stage p_k of tile p_tile
+    int p_tile = blockIdx.x, p_k = 0, p_i0 = 0, p_jstart = 0, p_nst = 0;
+    unsigned p_cnt = 0;
+    auto p_geometry = [&]() {
+        if (p_tile < ntiles) {
+            int a0, a1;
+            tile_lines(g, p_tile / g.gx, a0, a1);
+            p_i0 = (p_tile % g.gx) * kTmaStrip;
+            p_jstart = a0 - 1;
+            p_nst = (a1 - a0 + 2 + SR - 1) / SR;
+        }
+    };
+    auto issue_next = [&]() {
+        if (p_tile >= ntiles) return;
+        const int s = (int)(p_cnt % NST);
         mbar_expect_tx(&full[s], kStageBytes);
 #pragma unroll
         for (int a = 0; a < NIN; ++a)
             tma_load_2d(sbuf + (size_t)s * kStageDoubles + (size_t)a * SR * kTmaBoxX, &tm.m[a], &full[s],
-                        i0 - 2, jstart + k * SR);
+                        p_i0 - 2, p_jstart + p_k * SR);
+        ++p_cnt;
+        if (++p_k == p_nst) {
+            p_tile += gridDim.x;
+            p_k = 0;
+            p_geometry();
+        }
     };
     if (tid == 0) {
-        for (int k = 0; k < NST && k < nst; ++k) issue(k);
+        p_geometry();
+        for (int k = 0; k < NST; ++k) issue_next();
     }
 
     double acc[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+    unsigned c_cnt = 0;      // stages consumed so far (slot = c_cnt % NST, parity = (c_cnt / NST) & 1)
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = (tile % g.gx) * kTmaStrip;    // first output column of the strip
+    const int gi = i0 - 2 + 2 * tid;             // global column of this thread's pair
+    const bool outp = tid >= 1 && tid <= kStencilThreads - 2 && gi < g.nx;
+    int j0, j1;
+    tile_lines(g, tile / g.gx, j0, j1);
+    const int jstart = j0 - 1;
+    const int nrows = j1 - j0 + 2;
+    const int nst = (nrows + SR - 1) / SR;
     double up[VEC] = {0.0, 0.0}, cu[VEC] = {0.0, 0.0}, dn[VEC], cl = 0.0, cr = 0.0, dl, dr;
     double rawCu[NIN][VEC];
 #pragma unroll
@@ -151,9 +181,9 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, co
     const bool patch_hi = f.hi[0] != nullptr && j1 == g.ny;
     const int k_hi = (g.ny - jstart) / SR, rr_hi = (g.ny - jstart) % SR;
 
-    for (int k = 0; k < nst; ++k) {
-        const int s = k % NST;
-        mbar_wait(&full[s], (unsigned)((k / NST) & 1));
+    for (int k = 0; k < nst; ++k, ++c_cnt) {
+        const int s = (int)(c_cnt % NST);
+        mbar_wait(&full[s], (unsigned)((c_cnt / NST) & 1));
         double *st = sbuf + (size_t)s * kStageDoubles;
         // multi-GPU: the lines above / below this rank's slab come from the neighbours' halo buffers
         if ((patch_lo && k == 0) || (patch_hi && k == k_hi)) {
@@ -229,14 +259,15 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, co
             }
         }
         __syncthreads();   // every thread has read stage s
-        if (tid == 0 && k + NST < nst) {
+        if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + NST);
+            issue_next();  // refills slot s with the stage NST ahead (of this tile or of the CTA's next one)
         }
     }
+    }   // tiles of this CTA
 #ifdef KL_TRACE
     if (threadIdx.x == 0) {
-        const unsigned b = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned b = blockIdx.x;
         if (b < 16384) {
             g_trace[3 * b] = t_start;
             g_trace[3 * b + 1] = gtimer();
@@ -248,7 +279,7 @@ k_stencil_tma(const F f_in, const Geo g, const RedCtl rc, const PostAny post, co
         __shared__ double sm[NR * (kStencilThreads / 32)];
         __shared__ int s_flag;
         block_sum<NR, kStencilThreads>(acc, sm);
-        const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned nb = gridDim.x, bid = blockIdx.x;
         if (F::kLateWait && !waited) griddep_wait();
         if (grid_sum<NR, kStencilThreads>(acc, rc, nb, bid, &s_flag, sm)) {
             if (rc.peer) peer_allreduce_block<NR>(rc);

@@ -40,15 +40,14 @@ static __device__ __noinline__ void ts_tail_tT(const TsTail tt, const double *s,
     }
 }
 
+// one tall-skinny pass by the whole grid (body of k_ts_tma; also called three times in a row, with grid-wide
+// barriers in between, by the cooperative kernel k_cgs2_coop in kl_gmres.cu)
 template <bool UPDATE>
-__global__ void __launch_bounds__(kTsThreads, 2)
-k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, const int nc, const int RM,
-         const double *__restrict__ h_in, double *__restrict__ partials, unsigned int *counter,
-         double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
-         const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */,
-         const TsTail tt) {
-    if (flags && flags[I_CONV_AT] >= 0) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const size_t n, const int nc, const int RM,
+                                        const double *__restrict__ h_in, double *__restrict__ partials,
+                                        unsigned int *counter, double *__restrict__ out, const GmresDev &G, const int j,
+                                        const int h_mode, const long long tail0, const TsTail &tt,
+                                        unsigned char *smem_raw) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int RB = kTsRB * RM;                                  // rows per tile
     const int nslice = kTsWarps / RM;                            // column slices
@@ -188,6 +187,18 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
         __syncthreads();          // out[] was written by this block's warps
         ts_tail_tT(tt, out, nc);
     }
+}
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kTsThreads, 2)
+k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, const int nc, const int RM,
+         const double *__restrict__ h_in, double *__restrict__ partials, unsigned int *counter,
+         double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
+         const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */,
+         const TsTail tt) {
+    if (flags && flags[I_CONV_AT] >= 0) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ts_pass<UPDATE>(tmV, w, n, nc, RM, h_in, partials, counter, out, G, j, h_mode, tail0, tt, smem_raw);
 }
 
 inline size_t ts_tma_smem(int nc) {

@@ -152,3 +152,20 @@ def test_gmres_one_pass_step_bit_identical_to_two_kernels(kl, h, nx, ny, m):
         finally:
             h.set_option(5, 1)
         assert np.array_equal(e.history, g.history) and np.array_equal(e.x, g.x)
+
+
+@pytest.mark.parametrize("ns,m", [(100, 95), (300, 50), (512, 30)])
+def test_cooperative_cgs2_step_bit_identical_to_three_kernels(kl, h, ns, m):
+    """KL_OPT_COOP: the three tall-skinny passes of a CGS2 step as ONE cooperative kernel with two grid barriers
+    (k_cgs2_coop) against three separate launches.  Same device code and the same partial-sum order: identical bits."""
+    P = (8.2, 0.2)
+    b = h.apply(kl.stvec, np.ones(ns * ns), ns, ns)
+    g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+    h.set_option(20, 0)          # KL_OPT_COOP off
+    try:
+        u = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+    finally:
+        h.set_option(20, 1)
+    assert g.status == 0 and (g.n_out, g.restart_out) == (u.n_out, u.restart_out)
+    assert np.array_equal(g.history, u.history) and np.array_equal(g.x, u.x)
+    assert g.stats["kernel_launches"] < u.stats["kernel_launches"]
