@@ -236,27 +236,15 @@ __global__ void k_wy_xs(const GmresDev G, const HhWy W, const int k) {
 }
 
 // out = src - Y(:,0..nc-1) t ; src = e_row (mode 1) or [y(0..row-1); 0] (mode 2) ; dst: store or x += .
-// newcol != nullptr: column nc-1 of Y does not exist yet -- it is the reflector built from wsrc at the end of the
-// previous step, P = masked wsrc / ||.|| (gmres_hh.f90:315-318; pivot index nc-1, pivot value S_TMP1, norm S_NORM).
-// The kernel computes it on the fly, stores it to `newcol` and uses it, which saves the separate reflector kernel
-// (one launch and one read of w per step).
 template <int VEC>
 __global__ void __launch_bounds__(kTsThreads)
 k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, const double *__restrict__ t,
               const int src_mode, const long long row, const double *__restrict__ yv, double *dst,
-              const int add_to_dst, const size_t n, const int *__restrict__ flags,
-              double *newcol, const double *__restrict__ wsrc, const double *__restrict__ S) {
+              const int add_to_dst, const size_t n, const int *__restrict__ flags) {
     if (flags && flags[I_CONV_AT] >= 0) return;
     extern __shared__ double sh[];
     for (int c = threadIdx.x; c < nc; c += kTsThreads) sh[c] = t[c];
     __syncthreads();
-    const int nco = newcol ? nc - 1 : nc;        // columns read from Y
-    FastDiv fd;
-    double pv = 0.0;
-    if (newcol) {
-        fd.set(S[S_NORM]);
-        pv = S[S_TMP1];
-    }
     const size_t nchunk = n / VEC;
     for (size_t ch = (size_t)blockIdx.x * kTsThreads + threadIdx.x; ch < nchunk;
          ch += (size_t)gridDim.x * kTsThreads) {
@@ -268,7 +256,7 @@ k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, cons
             a[e] = src_mode == 1 ? (rr == row ? 1.0 : 0.0) : (rr < row ? yv[rr] : 0.0);
         }
         int c = 0;
-        for (; c + 8 <= nco; c += 8) {
+        for (; c + 8 <= nc; c += 8) {
             double v[8][VEC];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -287,7 +275,7 @@ k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, cons
                 for (int e = 0; e < VEC; ++e) a[e] = fma(hq, v[q][e], a[e]);
             }
         }
-        for (; c < nco; ++c) {
+        for (; c < nc; ++c) {
             const double *col = Y + (size_t)c * ldv + r;
             const double hq = -sh[c];
             if (VEC == 2) {
@@ -297,19 +285,6 @@ k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, cons
             } else {
                 a[0] = fma(hq, __ldg(col), a[0]);
             }
-        }
-        if (newcol) {
-            const long long piv = nc - 1;
-            const double hq = -sh[nc - 1];
-            double pn[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const long long tt = (long long)(r + e);
-                pn[e] = tt < piv ? 0.0 : fd.div(tt == piv ? pv : wsrc[r + e]);     // same arithmetic as PHhNewReflector
-                a[e] = fma(hq, pn[e], a[e]);
-            }
-            if (VEC == 2) stg2(newcol + r, pn[0], pn[VEC - 1]);
-            else newcol[r] = pn[0];
         }
         if (add_to_dst) {
 #pragma unroll
@@ -417,18 +392,17 @@ k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, c
 }
 
 static int launch_apply_wy(Ctx *c, const double *Y, size_t ldv, int nc, const double *t, int src_mode, long long row,
-                           const double *yv, double *dst, int add, size_t n, bool gated, double *newcol = nullptr,
-                           const double *wsrc = nullptr) {
+                           const double *yv, double *dst, int add, size_t n, bool gated) {
     const int vec = (n % 2 == 0 && ldv % 2 == 0) ? 2 : 1;
     size_t b = (n / vec + kTsThreads - 1) / kTsThreads;
     if (b > (size_t)kNumSM * 8) b = (size_t)kNumSM * 8;
     const size_t smem = sizeof(double) * (nc + 8);
     if (vec == 2)
         k_hh_apply_wy<2><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
-                                                                 gated ? c->d_I : nullptr, newcol, wsrc, c->d_S);
+                                                                 gated ? c->d_I : nullptr);
     else
         k_hh_apply_wy<1><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
-                                                                 gated ? c->d_I : nullptr, newcol, wsrc, c->d_S);
+                                                                 gated ? c->d_I : nullptr);
     c->stats.kernel_launches++;
     return KL_OK;
 }
@@ -559,20 +533,19 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
         }
         if (blocked) k_hh_first_wy<<<1, 32, 0, c->stream>>>(G, W, w);
         else k_hh_first<<<1, 32, 0, c->stream>>>(G, w);           // :250-252
-        if (!blocked) {
+        {
             PHhNewReflector f;                                // :253 P(:,1) = w / norm2(w)
             set_gate(f, c, false);
             f.w = w; f.p_out = Pm; f.S = c->d_S; f.piv = 0;
             KL_TRY(launch_pointwise(c, f, n, NoPost{}));
-        }   // (compact-WY mode: every reflector is written by the k_hh_apply_wy launch that first uses it)
+        }
         c->stats.kernel_launches++;
-        R.bytes += (blocked ? 40.0 : 56.0) * n;
+        R.bytes += 56.0 * n;
         for (int j = 0; j < m; ++j) {
             if (blocked) {
                 const int nc = j + 1;
                 // v_j = e_j - Y (T Ytop(j,:)^T) ; tvec = T Ytop(j,:)^T comes from the previous step's scalar kernel
-                // ... and P_j itself is built here from the previous step's w (gmres_hh.f90:315-318 / :253)
-                KL_TRY(launch_apply_wy(c, Pm, ldv, nc, W.tvec, 1, j, nullptr, vj, 0, n, true, Pm + (size_t)j * ldv, w));
+                KL_TRY(launch_apply_wy(c, Pm, ldv, nc, W.tvec, 1, j, nullptr, vj, 0, n, true));
                 if (prec) {
                     KL_TRY(op_apply(&P, vj, z, true));
                     KL_TRY(pc_apply(&P, z, w, aux, aux2, 0, true, NoPost{}));
@@ -586,9 +559,11 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
                 KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
                 k_hh_step_wy<<<1, kHhStepThreads, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
                 c->stats.kernel_launches += 1;
-                // (P_{j+1} is written by the next step's k_hh_apply_wy; the reflector after the last step is never
-                // applied -- the x update and calculate_verr use P_0 .. P_{n_out-1} only)
-                R.bytes += (24.0 * nc + 32.0 + 8.0 + (prec ? 32.0 : 16.0)) * n;
+                PHhNewReflector f;
+                set_gate(f, c, true, j, 1);
+                f.w = w; f.p_out = Pm + (size_t)(j + 1) * ldv; f.S = c->d_S; f.piv = (long long)j + 1;
+                KL_TRY(launch_pointwise(c, f, n, NoPost{}));
+                R.bytes += (24.0 * nc + 32.0 + 16.0 + (prec ? 32.0 : 16.0)) * n;
                 continue;
             }
             // v = P_0 ... P_j e_j  (:257-283): reflectors applied in the order j, j-1, ..., 0

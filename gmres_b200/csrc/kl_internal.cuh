@@ -137,7 +137,9 @@ struct kl_context_s {
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
-    int opt_persistent = 1;      // persistent CTAs in the TMA stencil kernels (KL_OPT_PERSISTENT)
+    int opt_persistent = 0;      // persistent CTAs in the TMA stencil kernels (KL_OPT_PERSISTENT): measured 4-8 % slower
+                                 // than one CTA per tile (static tile assignment balances worse than the hardware's
+                                 // dynamic CTA scheduling, profiles/r02_cta_timeline_persistent.txt): off by default
     int opt_persist_occ = 0;     // CTAs per SM of the persistent grid (0 = full occupancy)
     int opt_coop = 1;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP)
     int opt_reverse = 1;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE)
@@ -352,7 +354,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *smem /* K * NT
 // sums valid in thread 0.  Returns true in ALL threads of the last block to
 // arrive, after red[0..K) holds the grid sums.  The last block sums the partials
 // with all of its NT threads (thread t takes blocks t, t+NT, ... in increasing
-// order, four independent loads in flight), then combines the NT values in the
+// order, eight independent loads in flight), then combines the NT values in the
 // fixed order of block_sum: same launch configuration => same bits.  `nblocks`
 // is the linear grid size, `bid` the linear id, smem = K * NT/32 doubles.
 template <int K, int NT>
@@ -374,11 +376,12 @@ __device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc,
         const double *p = rc.partials + (size_t)k * kMaxBlocks;
         double a = 0.0;
         unsigned b = threadIdx.x;
-        for (; b + 3 * NT < nblocks; b += 4 * NT) {
-            const double t0 = __ldcg(p + b), t1 = __ldcg(p + b + NT), t2 = __ldcg(p + b + 2 * NT),
-                         t3 = __ldcg(p + b + 3 * NT);
-            a = ((a + t0) + t1) + t2;
-            a += t3;
+        for (; b + 7 * NT < nblocks; b += 8 * NT) {       // eight independent L2 loads in flight per thread
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = __ldcg(p + b + q * NT);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a += t[q];
         }
         for (; b < nblocks; b += NT) a += __ldcg(p + b);
         s[k] = a;

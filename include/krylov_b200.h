@@ -143,8 +143,9 @@ enum {
                                  its first, i.e. starts on what the first kernel left in L2 (tuning only)          */
     KL_OPT_COOP = 20,         /* 1 (default): on small grids (launch-bound, basis resident in L2) the three passes of the
                                  CGS2 orthogonalisation run as ONE cooperative kernel with two grid barriers        */
-    KL_OPT_PERSISTENT = 21,   /* 1 (default): the TMA stencil kernels run persistent CTAs (as many as fit on the GPU) that
-                                 loop over the tiles with the TMA ring running across tile boundaries; 0 = one CTA per tile */
+    KL_OPT_PERSISTENT = 21,   /* 1: the TMA stencil kernels run persistent CTAs (as many as fit on the GPU) that loop over
+                                 the tiles with the TMA ring running across tile boundaries; 0 (default) = one CTA per
+                                 tile -- the hardware's dynamic CTA scheduling balances better (measured)            */
     KL_OPT_PUSH_HALO = 16,    /* multi-GPU with peer memory: 1 (default) = the kernel that PRODUCES a vector pushes its
                                  boundary lines into the neighbours' halo slots (no halo kernel; the all-reduce that
                                  ends the kernel is the barrier); 0 = separate halo push before every operator apply */

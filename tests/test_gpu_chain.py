@@ -138,20 +138,24 @@ def test_gmres_one_pass_step_bit_identical_to_two_kernels(kl, h, nx, ny, m):
     same fma, the orthogonalisation kernels are the same ones: the residual history, H and x are bit-identical.
     Both with and without CUDA-graph replay of the restart cycle."""
     P = (8.2, 0.2)
-    for op in (kl.stvec, kl.aniso(1.0, 0.05)):
-        b = h.apply(op, np.ones(nx * ny), nx, ny)
-        run = lambda: h.gmres_mgsr_omp(op, b, m, 1e-9, kl.cbpr2, P, nx=nx, ny=ny)
-        g = run()
-        u = _no_chain(kl, h, run)
-        assert g.status == 0 and (g.n_out, g.restart_out) == (u.n_out, u.restart_out)
-        assert np.array_equal(g.history, u.history) and np.array_equal(g.x, u.x)
-        assert np.array_equal(g.final_err, u.final_err)
-        h.set_option(5, 0)          # KL_OPT_USE_GRAPH off: eager launches
-        try:
-            e = run()
-        finally:
-            h.set_option(5, 1)
-        assert np.array_equal(e.history, g.history) and np.array_equal(e.x, g.x)
+    h.set_option(2, 6)              # six restart cycles are enough to compare (the thin grids need hundreds to converge)
+    try:
+        for op in (kl.stvec, kl.aniso(1.0, 0.05)):
+            b = h.apply(op, np.ones(nx * ny), nx, ny)
+            run = lambda: h.gmres_mgsr_omp(op, b, m, 1e-9, kl.cbpr2, P, nx=nx, ny=ny)
+            g = run()
+            u = _no_chain(kl, h, run)
+            assert g.status in (0, 1) and (g.status, g.n_out, g.restart_out) == (u.status, u.n_out, u.restart_out)
+            assert g.history.size >= min(m, 20) and np.array_equal(g.history, u.history) and np.array_equal(g.x, u.x)
+            assert np.array_equal(g.final_err, u.final_err)
+            h.set_option(5, 0)          # KL_OPT_USE_GRAPH off: eager launches
+            try:
+                e = run()
+            finally:
+                h.set_option(5, 1)
+            assert np.array_equal(e.history, g.history) and np.array_equal(e.x, g.x)
+    finally:
+        h.set_option(2, 1000)
 
 
 @pytest.mark.parametrize("ns,m", [(100, 95), (300, 50), (512, 30)])
@@ -160,12 +164,16 @@ def test_cooperative_cgs2_step_bit_identical_to_three_kernels(kl, h, ns, m):
     (k_cgs2_coop) against three separate launches.  Same device code and the same partial-sum order: identical bits."""
     P = (8.2, 0.2)
     b = h.apply(kl.stvec, np.ones(ns * ns), ns, ns)
-    g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
-    h.set_option(20, 0)          # KL_OPT_COOP off
+    h.set_option(2, 8)           # eight restart cycles
     try:
-        u = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+        g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+        h.set_option(20, 0)          # KL_OPT_COOP off
+        try:
+            u = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+        finally:
+            h.set_option(20, 1)
     finally:
-        h.set_option(20, 1)
-    assert g.status == 0 and (g.n_out, g.restart_out) == (u.n_out, u.restart_out)
+        h.set_option(2, 1000)
+    assert g.status in (0, 1) and (g.status, g.n_out, g.restart_out) == (u.status, u.n_out, u.restart_out)
     assert np.array_equal(g.history, u.history) and np.array_equal(g.x, u.x)
     assert g.stats["kernel_launches"] < u.stats["kernel_launches"]
