@@ -624,7 +624,10 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     double bytes = 0.0;
     double *const w_base = w, *const z_base = z;
     // V_j = w/h, z = A V_j and w = cbpr2(z) as one temporally blocked pass (same decision on every rank)
-    const bool chain_step = fused && P.pc.kind == KL_PC_CBPR2 && chain_ok(&P, 2);
+    // (large grids only: the temporally blocked kernel's CTAs are 240 columns x 48 lines, which is 14 CTAs at 300^2 --
+    // there the two small stencil kernels, 76 CTAs each, are faster: 57 vs 61 us per step measured)
+    const bool chain_step = fused && P.pc.kind == KL_PC_CBPR2 && chain_ok(&P, 2) &&
+                            (size_t)P.nx * (size_t)(P.ny / c->nranks) >= ((size_t)1 << 20);
     const Cbpr2Coef cbc = chain_step ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
     const bool coop = cgs2_coop_ok(c, n, ldv, m);
     // One restart cycle = a fixed sequence of launches (every pointer, column count and step index is known on

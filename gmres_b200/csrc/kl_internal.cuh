@@ -932,7 +932,9 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
             long tiles = (long)grid.x * grid.y;                                                     \
             if (!c->opt_persistent) res = tiles;                                                    \
             if (res > kMaxBlocks) res = kMaxBlocks;                                                 \
-            grid = dim3((unsigned)(tiles < res ? tiles : res));                                     \
+            /* balanced: every CTA gets the same number of tiles (+-1), so that they all finish together */ \
+            const long rounds = (tiles + res - 1) / res;                                            \
+            grid = dim3((unsigned)((tiles + rounds - 1) / rounds));                                 \
         }                                                                                           \
         cfg.gridDim = grid;                                                                         \
         cfg.dynamicSmemBytes = SMEM;                                                                \

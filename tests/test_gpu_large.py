@@ -181,3 +181,32 @@ def test_gmres_mgsr_300_at_the_drivers_tolerance(env, ko, ortho):
     assert g.status == 0 and abs(gi - oi) <= 1
     assert hist_rel(g.history[:m], o.history[:m]) < 1e-10 and hist_norm(g.history[:k], o.history[:k]) < 1e-10
     assert np.abs(g.x - o.x).max() < 1e-9 and np.abs(g.x - 1).max() < 1e-10
+
+
+def test_gmres_selective_fast_mode_4096(env):
+    """KL_ORTHO_CGS2_SELECTIVE with eta = 0.3, the documented fast mode (scripts/eta_sweep.py: at 1024^2 and 2048^2 the
+    iteration counts to rtol 1e-8 are IDENTICAL to the always-twice scheme, 5669 and 19 260, with nearly every second
+    pass skipped, 1.4x the iterations/s, ||I - V^T V||_F 2e-12 instead of 1e-15): one full m = 95 cycle at BASELINE
+    config 3's size against the always-twice result."""
+    kl, h, torch = env
+    n, m = 4096, 95
+    b = h.apply(kl.stvec, torch.ones(n * n, dtype=torch.float64, device="cuda"), n, n)
+    h.set_option(2, 1)
+    h.set_option(3, 1)
+    try:
+        a = h.gmres_mgsr_omp(kl.stvec, b, m, 0.0, kl.cbpr2, P, nx=n, ny=n)
+        h.set_ortho(2)
+        h.set_option(11, 300)
+        s = h.gmres_mgsr_omp(kl.stvec, b, m, 0.0, kl.cbpr2, P, nx=n, ny=n)
+    finally:
+        h.set_ortho(1)
+        h.set_option(11, 707)
+        h.set_option(3, 0)
+        h.set_option(2, 1000)
+    print(f"selective eta=0.3 4096^2: skipped {s.stats['reorth_skipped']} of {m}, history rel {hist_rel(s.history, a.history):.2e}, "
+          f"orth {s.stats['orth_frobenius']:.2e} (always twice {a.stats['orth_frobenius']:.2e}), "
+          f"ms {s.stats['solve_ms']:.1f} vs {a.stats['solve_ms']:.1f}")
+    assert s.n_out == a.n_out == m and s.stats["reorth_skipped"] >= m // 2
+    assert hist_rel(s.history, a.history) < 1e-9 and hist_norm(s.history, a.history) < 1e-10
+    assert s.stats["orth_frobenius"] < 1e-9 and float((s.x - a.x).abs().max()) < 1e-9
+    assert s.stats["solve_ms"] < 0.85 * a.stats["solve_ms"]
