@@ -141,8 +141,10 @@ struct kl_context_s {
                                  // than one CTA per tile (static tile assignment balances worse than the hardware's
                                  // dynamic CTA scheduling, profiles/r02_cta_timeline_persistent.txt): off by default
     int opt_persist_occ = 0;     // CTAs per SM of the persistent grid (0 = full occupancy)
-    int opt_coop = 1;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP)
-    int opt_reverse = 1;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE)
+    int opt_coop = 0;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP): measured 4 % SLOWER than
+                                 // three graph-replayed launches at 300^2 (fewer co-resident CTAs, two grid barriers): off
+    int opt_reverse = 0;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE): no
+                                 // measurable L2 reuse on B200 (264.0 vs 265.0 us at 8 GPUs): off by default
     int opt_stencil_stagger = 0; // staggered tile heights (KL_OPT_STENCIL_STAGGER): measured neutral, off by default
     int opt_stencil_tail = -1;  // lines per CTA in the tapered tail (-1 auto, 0 off), KL_OPT_STENCIL_TAIL
     int opt_pdl = 1;            // programmatic dependent launch between the fused CG kernels (KL_OPT_PDL)
@@ -827,7 +829,8 @@ inline bool stencil_geometry(int nx, int ny, int strip, long resident, Geo *g, d
     // tail of about a third of that; on the 2048-line slab of the 8-GPU strong-scaling run 32-line CTAs (4224 CTAs)
     // measured 3 % faster per iteration than 64-line ones, while below 32 lines the per-CTA overhead and the two
     // halo lines per CTA cost more than the tail (scripts/slab_sweep.py).
-    const long want = (long)kNumSM * (gx >= 32 ? 28 : 8);
+    const long want = (long)kNumSM * (gx >= 32 ? 16 : 8);     // (with the tapered tail, 57-line tiles measured 1 % faster
+                                                               // than 33-line ones on the 2048-line slab of the 8-GPU run)
     long rows = ((long)ny * gx + want - 1) / want;
     if (rows < 8) rows = 8;
     if (rows > 128) rows = 128;            // 16384^2 on one GPU: 128-line tiles with a 32-line tail measured 2 % faster

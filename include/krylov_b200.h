@@ -139,10 +139,11 @@ enum {
     KL_OPT_STENCIL_STAGGER = 18, /* 1: CTA heights of the stencil kernels staggered (5/8 .. 11/8 of the mean) so that CTAs
                                  do not start and drain in lockstep waves; 0 (default): equal heights -- measured
                                  neutral on B200 (profiles/r02_cta_timeline.md)                                   */
-    KL_OPT_REVERSE = 19,      /* 1 (default): the second kernel of a CG iteration marches the grid from its last lines to
-                                 its first, i.e. starts on what the first kernel left in L2 (tuning only)          */
-    KL_OPT_COOP = 20,         /* 1 (default): on small grids (launch-bound, basis resident in L2) the three passes of the
-                                 CGS2 orthogonalisation run as ONE cooperative kernel with two grid barriers        */
+    KL_OPT_REVERSE = 19,      /* 1: the second kernel of a CG iteration marches the grid from its last lines to its first,
+                                 i.e. starts on what the first kernel left in L2; 0 (default): measured neutral     */
+    KL_OPT_COOP = 20,         /* 1: on small grids (launch-bound, basis resident in L2) the three passes of the CGS2
+                                 orthogonalisation run as ONE cooperative kernel with two grid barriers; 0 (default):
+                                 three graph-replayed launches measured 4 % faster at 300^2                         */
     KL_OPT_PERSISTENT = 21,   /* 1: the TMA stencil kernels run persistent CTAs (as many as fit on the GPU) that loop over
                                  the tiles with the TMA ring running across tile boundaries; 0 (default) = one CTA per
                                  tile -- the hardware's dynamic CTA scheduling balances better (measured)            */

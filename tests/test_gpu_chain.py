@@ -167,12 +167,12 @@ def test_cooperative_cgs2_step_bit_identical_to_three_kernels(kl, h, ns, m):
     b = h.apply(kl.stvec, np.ones(ns * ns), ns, ns)
     h.set_option(2, 8)           # eight restart cycles
     try:
-        g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
-        h.set_option(20, 0)          # KL_OPT_COOP off
+        u = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+        h.set_option(20, 1)          # KL_OPT_COOP on (off by default: measured slower than graph-replayed launches)
         try:
-            u = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
+            g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-9, kl.cbpr2, P)
         finally:
-            h.set_option(20, 1)
+            h.set_option(20, 0)
     finally:
         h.set_option(2, 1000)
     assert g.status in (0, 1) and (g.status, g.n_out, g.restart_out) == (u.status, u.n_out, u.restart_out)
