@@ -78,7 +78,7 @@ struct ChainRing {
     static constexpr int SR = C::SR;
     static constexpr int NST = C::NST;
     static constexpr int NR = SR * NST;
-    static constexpr int RET = (C::L + SR - 1) / SR;
+    static constexpr int RET = (C::LAG * C::L + SR - 1) / SR;
     static_assert(6 % SR == 0, "a hexad must hold whole stages");
     static_assert(NR % 6 == 0, "ring must hold whole hexads");
     static_assert(NST - RET >= 2, "ring too shallow");
@@ -97,6 +97,25 @@ struct ChainBase {
     static constexpr int NC = NC_;
     static constexpr int NRED = NRED_;
     static constexpr int NSIDE = 0;     // point-wise side inputs of the last level, prefetched 2 lines ahead
+    // LAG: how many lines level l runs behind level l-1.  With LAG = 1 level l consumes the line level l-1
+    // produced in the SAME march step, so a step is one dependent chain of 7L FP64 operations (~250 cycles of
+    // latency at L = 4 with 4 warps per scheduler to hide it: the round-1 kernel ran the FP64 pipe at 44 %).
+    // With LAG = 2 every level reads only lines finished in EARLIER steps: the L levels of a step are
+    // independent instruction streams (processed last level first, so a level reads its predecessor's window
+    // before the predecessor overwrites the oldest line -- still 3 lines per level).  Price: L more march steps
+    // per CTA and 2L instead of L lines of ring retention, which is why multi-input chains keep LAG = 1.
+    // Measured at 8192^2 (profiles/r02_bench_chain_cheb8192.txt): LAG 2 wins only at L = 2 (232 vs 245 us); from
+    // L = 4 on its extra address arithmetic and spills under the register cap cost more than the latency it hides
+    // (L = 5: 667 vs 524 us).
+#ifdef KL_CHAIN_LAG
+    static constexpr int LAG = NIN_ == 1 ? KL_CHAIN_LAG : 1;
+#else
+    static constexpr int LAG = (NIN_ == 1 && L_ == 2) ? 2 : 1;
+#endif
+    // LEAN: interior CTAs run their middle hexads through a copy of the march without out-of-domain masks (see
+    // k_chain_tma).  Pays from L = 3 on (L - 1 masked levels; 322 -> 292 us at L = 3, 703 -> 643 us at L = 6); at
+    // L <= 2 and for the multi-input chains the checked first hexad it needs costs more than the masks (+9 %).
+    static constexpr bool LEAN = NIN_ == 1 && L_ >= 3;
     // Two columns per thread.  A four-column variant (half the shuffles and per-line overhead per point, but
     // ~160 registers at L = 2, i.e. 3 CTAs per SM instead of 6) measured 10-50 % slower: these kernels are
     // dependent FP64 chains behind a shuffle and live on thread-level parallelism.
@@ -155,7 +174,8 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     using RG = ChainRing<C>;
     constexpr int NSIDE = C::NSIDE, NSD = NSIDE > 0 ? NSIDE : 1;
     constexpr int H = D::H, WW = D::WW, BWP = D::BWP;
-    constexpr int SR = RG::SR, NST = RG::NST, NR = RG::NR, RET = RG::RET;
+    constexpr int SR = RG::SR, NST = RG::NST, NR = RG::NR, RET = RG::RET, LAG = C::LAG;
+    static_assert(LAG == 1 || LAG == 2, "level lag");
     constexpr unsigned kStageBytes = NIN * SR * BWP * sizeof(double);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -172,7 +192,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     const int j0 = blockIdx.y * g.rows;
     const int j1 = min(j0 + g.rows, g.ny);
     const int jstart = j0 - L;                       // grid line of march step 0
-    const int T = (j1 - j0) + 2 * L;                 // march steps
+    const int T = (j1 - j0) + L + LAG * L;           // march steps (level L emits line R - LAG*L)
     const int nstg = (T + SR - 1) / SR;
 
     if (tid == 0) {
@@ -217,16 +237,21 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         for (int s = 0; s < 3; ++s) SD[a][s][0] = SD[a][s][1] = 0.0;
 
     const double *tb = ring + bc;     // this thread's pair in ring line 0 of input 0
-    const double *cur = tb, *prev = tb;
+    const double *cur = tb, *prev = tb, *prev2 = tb;
     int q = 0;                        // stage of the current march step
 
-    // one march step; PH = step index mod 6 (compile time), t = step index
-    auto step = [&](auto ph, const int t) {
+    // one march step; PH = step index mod 6 (compile time), t = step index.  LEAN: the step belongs to a hexad
+    // in which the last level's line is inside [j0, j1) for all six steps, of a CTA whose windows and lines all
+    // lie inside the domain (see `lean_cta` below): no out-of-domain masks, no halo-line patch, the output
+    // predicate of the last level is the loop-invariant `outlane` (12 FSEL and ~12 ISETP/PLOP3 less per step at
+    // L = 4).  Everything else -- first and last hexads, CTAs on the domain edge -- takes the generic path.
+    auto step = [&](auto ph, auto lean_c, const int t) {
         constexpr int PH = decltype(ph)::value;
+        constexpr bool LEAN = decltype(lean_c)::value;
         const int R = jstart + t;     // grid line entering level 0
         if (NSIDE > 0) {
             // the last level reaches line R - L + 2 two steps from now: start its point-wise loads today
-            const int rho2 = R - L + 2;
+            const int rho2 = R - LAG * L + 2;
             if (outlane && rho2 >= j0 && rho2 < j1) {
 #pragma unroll
                 for (int a = 0; a < NSIDE; ++a) {
@@ -237,9 +262,9 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             }
         }
         // ---- level 0 -------------------------------------------------------
-        {
+        auto level_zero = [&]() {
             double raw[NIN][2];
-            if (MG && ((R < 0 && f.lo[0] != nullptr) || (R >= g.ny && f.hi[0] != nullptr))) {
+            if (MG && !LEAN && ((R < 0 && f.lo[0] != nullptr) || (R >= g.ny && R < g.ny + L && f.hi[0] != nullptr))) {
                 // multi-GPU: this line belongs to a neighbour rank; TMA delivered zeros, take it from the halo
                 // buffer and patch the ring (every thread re-reads only its own column pair later)
 #pragma unroll
@@ -260,15 +285,18 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             }
             const bool out = outlane && R >= j0 && R < j1;
             f.level0(out, (size_t)R * g.nx + gc, raw, U[0][PH % 3], CC[0][PH % 2], acc);
-        }
-        // ---- levels 1..L ---------------------------------------------------
+        };
+        if (LAG == 1) level_zero();
+        // ---- levels 1..L (LAG 1: ascending, each consumes what its predecessor just produced; LAG 2: descending,
+        //      all independent, each reads its predecessor's window before the predecessor rotates it) -------------
 #pragma unroll
-        for (int l = 1; l <= L; ++l) {
-            const int sl_cu = (PH - l + 12) % 3;          // slot of line R-l in U[l-1]
-            const int sl_up = (PH - l - 1 + 12) % 3;      // line R-l-1
-            const int sl_dn = (PH - l + 1 + 12) % 3;      // line R-l+1
-            const int cs_in = (PH - l + 12) % 2;          // slot of line R-l in CC[l-1]
-            const int rho = R - l;
+        for (int li = 0; li < L; ++li) {
+            const int l = LAG == 1 ? li + 1 : L - li;
+            const int sl_cu = (PH - LAG * l + 24) % 3;          // slot of line rho = R - LAG*l in U[l-1]
+            const int sl_up = (PH - LAG * l - 1 + 24) % 3;      // line rho-1
+            const int sl_dn = (PH - LAG * l + 1 + 24) % 3;      // line rho+1
+            const int cs_in = (PH - LAG * l + 24) % 2;          // slot of line rho in CC[l-1]
+            const int rho = R - LAG * l;
             const double(&cu)[2] = U[l - 1][sl_cu];
             const double(&up)[2] = U[l - 1][sl_up];
             const double(&dn)[2] = U[l - 1][sl_dn];
@@ -277,12 +305,15 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             double au[2];
             au[0] = apply5c<OPK>(cu[0], lf, cu[1], dn[0], up[0], f.coef);
             au[1] = apply5c<OPK>(cu[1], cu[0], rt, dn[1], up[1], f.coef);
-            // raw inputs of line R-l from the ring (previous hexad when PH < l)
-            const double *rb = (PH - l >= 0) ? cur + (size_t)(PH - l) * BWP : prev + (size_t)(6 + PH - l) * BWP;
+            // raw inputs of line rho from the ring (an earlier hexad when PH < LAG*l)
+            const int kb = PH - LAG * l;
+            const double *rb = kb >= 0 ? cur + (size_t)(kb >= 0 ? kb : 0) * BWP
+                                       : (kb >= -6 ? prev + (size_t)(kb >= -6 ? 6 + kb : 0) * BWP
+                                                   : prev2 + (size_t)(12 + kb >= 0 ? 12 + kb : 0) * BWP);
             auto rawget = [&](int a) -> double2 {
                 return *reinterpret_cast<const double2 *>(rb + (size_t)a * NR * BWP);
             };
-            const bool out = outlane && rho >= j0 && rho < j1;
+            const bool out = (LEAN && l == L) ? outlane : (outlane && rho >= j0 && rho < j1);
             double un[2], cn[NC][2];
             double sd[NSD][2];
 #pragma unroll
@@ -292,10 +323,10 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             }
             f.level(l, out, (size_t)rho * g.nx + gc, cu, au, CC[l - 1][cs_in], rawget, sd, un, cn, acc);
             if (l < L) {
-                const bool rowin = rho >= g.row_lo && rho < g.row_hi;
-                const bool m0 = rowin & colin0, m1 = rowin & colin1;
-                const int sl_new = (PH - l + 12) % 3;     // line R-l in U[l]
-                const int cs_new = (PH - l + 12) % 2;
+                const bool rowin = LEAN || (rho >= g.row_lo && rho < g.row_hi);
+                const bool m0 = LEAN || (rowin & colin0), m1 = LEAN || (rowin & colin1);
+                const int sl_new = (PH - LAG * l + 24) % 3;     // line rho in U[l]
+                const int cs_new = (PH - LAG * l + 24) % 2;
                 U[l < L ? l : 0][sl_new][0] = m0 ? un[0] : 0.0;
                 U[l < L ? l : 0][sl_new][1] = m1 ? un[1] : 0.0;
 #pragma unroll
@@ -305,17 +336,18 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
                 }
             }
         }
+        if (LAG != 1) level_zero();
     };
 
     // one stage boundary check + step, phase PH.  CHECK = false: the step is known to exist (whole hexads of the
     // main loop) -- no per-step bound test, so the march body is straight-line code and the shuffles need no
     // reconvergence scaffolding (WARPSYNC / ENDCOLLECTIVE around every SHFL of a conditionally executed step)
-    auto phase = [&](auto ph, auto chk, const int t) {
+    auto phase = [&](auto ph, auto chk, auto lean_c, const int t) {
         constexpr int PH = decltype(ph)::value;
         constexpr bool CHECK = decltype(chk)::value;
         if (!CHECK || t < T) {
             if (PH % SR == 0) mbar_wait(&full[q % NST], (unsigned)((q / NST) & 1));
-            step(ph, t);
+            step(ph, lean_c, t);
             if (PH % SR == SR - 1) {
                 // this warp is done with stage q - RET (its lines are more than L behind the next step)
                 __syncwarp();
@@ -335,28 +367,72 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     using TT = std::true_type;
     using FF = std::false_type;
 
+    // a CTA is lean when every column of its four windows and every line it touches is inside the domain
+    const bool lean_cta = i0 - H >= 0 && i0 - H + kChainWarps * WW + 2 * H <= g.nx && jstart >= 0 && jstart + T <= g.ny;
+    constexpr int kLeanT0 = L + LAG * L;      // first step whose last-level line is >= j0
+
+    // Two copies of the march per kernel: a fast one for whole hexads and the generic, step-by-step checked one.
+    //   LEAN kernels : fast = lean hexads of interior CTAs ; generic = first hexads, the partial last one, edge CTAs
+    //   others       : fast = every whole hexad (generic but unchecked) ; checked = the partial last hexad
+    using LeanT = std::integral_constant<bool, C::LEAN>;
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    using I4 = std::integral_constant<int, 4>;
+    using I5 = std::integral_constant<int, 5>;
     int hs = 0;   // ring line of the current hexad
-    int t0 = 0;
-    for (; t0 + 6 <= T; t0 += 6) {
+    auto set_hexad = [&]() {
         cur = tb + (size_t)hs * BWP;
         prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
-        phase(std::integral_constant<int, 0>{}, FF{}, t0 + 0);
-        phase(std::integral_constant<int, 1>{}, FF{}, t0 + 1);
-        phase(std::integral_constant<int, 2>{}, FF{}, t0 + 2);
-        phase(std::integral_constant<int, 3>{}, FF{}, t0 + 3);
-        phase(std::integral_constant<int, 4>{}, FF{}, t0 + 4);
-        phase(std::integral_constant<int, 5>{}, FF{}, t0 + 5);
-        hs += 6;
-        if (hs == NR) hs = 0;
-    }
-    if (t0 < T) {      // the last, partial hexad
-        cur = tb + (size_t)hs * BWP;
-        prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
-        phase(std::integral_constant<int, 0>{}, TT{}, t0 + 0);
-        phase(std::integral_constant<int, 1>{}, TT{}, t0 + 1);
-        phase(std::integral_constant<int, 2>{}, TT{}, t0 + 2);
-        phase(std::integral_constant<int, 3>{}, TT{}, t0 + 3);
-        phase(std::integral_constant<int, 4>{}, TT{}, t0 + 4);
+        prev2 = NR >= 12 ? tb + (size_t)(hs >= 12 ? hs - 12 : hs + NR - 12) * BWP : tb;
+    };
+    if (C::LEAN) {
+        for (int t0 = 0; t0 < T; t0 += 6) {
+            set_hexad();
+#ifdef KL_CHAIN_LEAN_ONLY      /* instruction counting only (scripts/sass_loops.py): drops the generic copy */
+            if (true) {
+#else
+            if (lean_cta && t0 >= kLeanT0 && t0 + 6 <= T) {
+#endif
+                phase(I0{}, FF{}, LeanT{}, t0 + 0);
+                phase(I1{}, FF{}, LeanT{}, t0 + 1);
+                phase(I2{}, FF{}, LeanT{}, t0 + 2);
+                phase(I3{}, FF{}, LeanT{}, t0 + 3);
+                phase(I4{}, FF{}, LeanT{}, t0 + 4);
+                phase(I5{}, FF{}, LeanT{}, t0 + 5);
+            } else {
+                phase(I0{}, TT{}, FF{}, t0 + 0);
+                phase(I1{}, TT{}, FF{}, t0 + 1);
+                phase(I2{}, TT{}, FF{}, t0 + 2);
+                phase(I3{}, TT{}, FF{}, t0 + 3);
+                phase(I4{}, TT{}, FF{}, t0 + 4);
+                phase(I5{}, TT{}, FF{}, t0 + 5);
+            }
+            hs += 6;
+            if (hs == NR) hs = 0;
+        }
+    } else {
+        int t0 = 0;
+        for (; t0 + 6 <= T; t0 += 6) {
+            set_hexad();
+            phase(I0{}, FF{}, FF{}, t0 + 0);
+            phase(I1{}, FF{}, FF{}, t0 + 1);
+            phase(I2{}, FF{}, FF{}, t0 + 2);
+            phase(I3{}, FF{}, FF{}, t0 + 3);
+            phase(I4{}, FF{}, FF{}, t0 + 4);
+            phase(I5{}, FF{}, FF{}, t0 + 5);
+            hs += 6;
+            if (hs == NR) hs = 0;
+        }
+        if (t0 < T) {
+            set_hexad();
+            phase(I0{}, TT{}, FF{}, t0 + 0);
+            phase(I1{}, TT{}, FF{}, t0 + 1);
+            phase(I2{}, TT{}, FF{}, t0 + 2);
+            phase(I3{}, TT{}, FF{}, t0 + 3);
+            phase(I4{}, TT{}, FF{}, t0 + 4);
+        }
     }
 
     if (NRED > 0) {
@@ -376,7 +452,10 @@ template <int L>
 inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid) {
     const long gx = (nx + ChainDims<L>::STRIP - 1) / ChainDims<L>::STRIP;
     if (gx > kMaxBlocks) return false;
-    long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : 24 * L;
+    // measured at 8192^2 (profiles/r02_bench_chain_cheb8192.txt): L <= 3 is flat between 24L and 64L lines; from
+    // L = 4 on longer marches pay (fewer redundant lines, more lean hexads): L = 4: 422 / 400 / 379 us at 96 / 144 /
+    // 192 lines, L = 6: 654 / 634 / 599 us at 144 / 144 / 192
+    long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : (L <= 3 ? 24 * L : (48 * L < 240 ? 48 * L : 240));
     if (rows < 24) rows = 24;
     const long want = (long)kNumSM * 4;
     while (rows > 12 * L && rows > 16 && gx * ((ny + rows - 1) / rows) < want) rows -= 6;

@@ -301,7 +301,9 @@ struct FastDiv {
     }
     // two quotients with ONE warp-wide test for the rare operands (zero, tiny, huge, NaN): the common path is
     // straight-line code instead of a divergence scaffold (BSSY / BRA / BSYNC) per division.  All 32 lanes of the
-    // warp must call it together.
+    // warp must call it together.  The range test 2^-700 <= |x| < 2^700 runs on the exponent field in the integer
+    // pipe (one shift-add and one unsigned compare per operand; `ok` is folded into the bounds by set()) instead
+    // of two DSETP per operand on the half-rate FP64 pipe.
     __device__ __forceinline__ void div2(double x0, double x1, double &o0, double &o1) const {
         const double a0 = x0 * rd, a1 = x1 * rd;
         double r0 = fma(-a0, d, x0), r1 = fma(-a1, d, x1);
@@ -310,11 +312,12 @@ struct FastDiv {
         r1 = fma(-q1, d, x1);
         q0 = fma(r0, rd, q0);
         q1 = fma(r1, rd, q1);
-        const double ax0 = fabs(x0), ax1 = fabs(x1);
-        const bool rare = !(ok && ax0 >= 0x1p-700 && ax0 <= 0x1p700 && ax1 >= 0x1p-700 && ax1 <= 0x1p700);
-        if (__any_sync(0xffffffffu, rare)) {
-            if (!(ok && ax0 >= 0x1p-700 && ax0 <= 0x1p700)) q0 = (x0 == 0.0 && ok) ? a0 : slow_div(x0, d);
-            if (!(ok && ax1 >= 0x1p-700 && ax1 <= 0x1p700)) q1 = (x1 == 0.0 && ok) ? a1 : slow_div(x1, d);
+        const unsigned lo2 = ok ? 2u * 0x14300000u : 0xffffffffu, span = ok ? 2u * (0x6bb00000u - 0x14300000u) : 0u;
+        const bool in0 = (((unsigned)__double2hiint(x0) << 1) - lo2) < span;
+        const bool in1 = (((unsigned)__double2hiint(x1) << 1) - lo2) < span;
+        if (__any_sync(0xffffffffu, !(in0 && in1))) {
+            if (!in0) q0 = (x0 == 0.0 && ok) ? a0 : slow_div(x0, d);
+            if (!in1) q1 = (x1 == 0.0 && ok) ? a1 : slow_div(x1, d);
         }
         o0 = q0;
         o1 = q1;
