@@ -449,13 +449,14 @@ int tmap_encode_box(Ctx *c, CUtensorMap *out, const double *base, int nx, int ny
 
 // lines per CTA: the redundant work is 2L / rows; keep it below ~10 % but leave >= ~3 CTAs per SM.
 template <int L>
-inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid) {
+inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid, bool single_input = false) {
     const long gx = (nx + ChainDims<L>::STRIP - 1) / ChainDims<L>::STRIP;
     if (gx > kMaxBlocks) return false;
-    // measured at 8192^2 (profiles/r02_bench_chain_cheb8192.txt): L <= 3 is flat between 24L and 64L lines; from
-    // L = 4 on longer marches pay (fewer redundant lines, more lean hexads): L = 4: 422 / 400 / 379 us at 96 / 144 /
-    // 192 lines, L = 6: 654 / 634 / 599 us at 144 / 144 / 192
-    long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : (L <= 3 ? 24 * L : (48 * L < 240 ? 48 * L : 240));
+    // measured at 8192^2 (profiles/r02_chain_rows_sweep.txt): L <= 3 is flat between 24L and 64L lines; from L = 4 on
+    // the single-input chains like longer marches (fewer redundant lines, more lean hexads): L = 4: 392 / 384 / 381 /
+    // 398 / 429 us at 96 / 160 / 192 / 224 / 256 lines, L = 6: 683 / 628 / 596 / 630 / 648 us.  The multi-input chains
+    // (continuation chunks, BiCGSTAB) run 2-3 CTAs per SM and lose more to the ragged last wave than they gain.
+    long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : ((L <= 3 || !single_input) ? 24 * L : 192);
     if (rows < 24) rows = 24;
     const long want = (long)kNumSM * 4;
     while (rows > 12 * L && rows > 16 && gx * ((ny + rows - 1) / rows) < want) rows -= 6;
@@ -480,7 +481,7 @@ inline int launch_chain(Ctx *c, const kl_operator_t *op, C f, int nx, int ny, co
     using RG = ChainRing<C>;
     ChainGeo g;
     dim3 grid;
-    if (!chain_geometry<L>(c, nx, ny, &g, &grid))
+    if (!chain_geometry<L>(c, nx, ny, &g, &grid, C::NIN == 1))
         return c->fail(KL_ERR_UNSUPPORTED, "grid too wide for the reduction buffer");
     // lines of the neighbour ranks are unknowns too (recomputed redundantly level by level)
     if (f.lo[0]) g.row_lo = -L;
