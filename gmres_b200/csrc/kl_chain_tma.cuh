@@ -79,8 +79,9 @@ struct ChainRing {
     static constexpr int NST = C::NST;
     static constexpr int NR = SR * NST;
     static constexpr int RET = (C::LAG * C::L + SR - 1) / SR;
-    static_assert(6 % SR == 0, "a hexad must hold whole stages");
-    static_assert(NR % 6 == 0, "ring must hold whole hexads");
+    static constexpr int P = 6;                         // unroll period of the march = lcm(3 field slots, 2 carried slots)
+    static_assert(P % SR == 0, "an unroll period must hold whole stages");
+    static_assert(NR % P == 0, "ring must hold whole periods");
     static_assert(NST - RET >= 2, "ring too shallow");
     static constexpr size_t bytes = (size_t)C::NIN * NR * ChainDims<C::L>::BWP * sizeof(double) + 2 * NST * 8 + 64;
 };
@@ -176,6 +177,13 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     constexpr int H = D::H, WW = D::WW, BWP = D::BWP;
     constexpr int SR = RG::SR, NST = RG::NST, NR = RG::NR, RET = RG::RET, LAG = C::LAG;
     static_assert(LAG == 1 || LAG == 2, "level lag");
+    // Unroll period P and carried-value slots CCS.  The carried values of a point (e.g. the Chebyshev direction d)
+    // are consumed LAG steps after they were produced: with LAG 1 the consumer runs after the producer within a
+    // step (old and new value live at once), with LAG 2 the value must survive two steps -- two slots either way,
+    // rotation period lcm(3, 2) = 6.  (A period-3 march needs a third carried slot, 4 L NC more registers, which the
+    // 128-register budget at L = 3, 4 does not have.)
+    constexpr int P = RG::P, CCS = 2;
+    constexpr int NB = (LAG * L + P - 1) / P;      // how many periods back raw inputs are re-read
     constexpr unsigned kStageBytes = NIN * SR * BWP * sizeof(double);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -219,13 +227,13 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
 #pragma unroll
     for (int k = 0; k < NR_; ++k) acc[k] = 0.0;
     // register windows: U[l][slot][e] = field of level l (l < L), 3 lines ; CC[l][slot][k][e] carried values, 2 lines
-    double U[L][3][2], CC[L][2][NC][2];
+    double U[L][3][2], CC[L][CCS][NC][2];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) U[l][s][0] = U[l][s][1] = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < CCS; ++s)
 #pragma unroll
             for (int k = 0; k < NC; ++k) CC[l][s][k][0] = CC[l][s][k][1] = 0.0;
     }
@@ -237,7 +245,10 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
         for (int s = 0; s < 3; ++s) SD[a][s][0] = SD[a][s][1] = 0.0;
 
     const double *tb = ring + bc;     // this thread's pair in ring line 0 of input 0
-    const double *cur = tb, *prev = tb, *prev2 = tb;
+    const double *rbase[NB + 1];      // ring line of the current period [0] and of the NB periods before it
+#pragma unroll
+    for (int k = 0; k <= NB; ++k) rbase[k] = tb;
+    const double *&cur = rbase[0];
     int q = 0;                        // stage of the current march step
 
     // one march step; PH = step index mod 6 (compile time), t = step index.  LEAN: the step belongs to a hexad
@@ -284,7 +295,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
                 }
             }
             const bool out = outlane && R >= j0 && R < j1;
-            f.level0(out, (size_t)R * g.nx + gc, raw, U[0][PH % 3], CC[0][PH % 2], acc);
+            f.level0(out, (size_t)R * g.nx + gc, raw, U[0][PH % 3], CC[0][PH % CCS], acc);
         };
         if (LAG == 1) level_zero();
         // ---- levels 1..L (LAG 1: ascending, each consumes what its predecessor just produced; LAG 2: descending,
@@ -295,7 +306,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             const int sl_cu = (PH - LAG * l + 24) % 3;          // slot of line rho = R - LAG*l in U[l-1]
             const int sl_up = (PH - LAG * l - 1 + 24) % 3;      // line rho-1
             const int sl_dn = (PH - LAG * l + 1 + 24) % 3;      // line rho+1
-            const int cs_in = (PH - LAG * l + 24) % 2;          // slot of line rho in CC[l-1]
+            const int cs_in = (PH - LAG * l + 24) % CCS;        // slot of line rho in CC[l-1]
             const int rho = R - LAG * l;
             const double(&cu)[2] = U[l - 1][sl_cu];
             const double(&up)[2] = U[l - 1][sl_up];
@@ -307,9 +318,8 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
             au[1] = apply5c<OPK>(cu[1], cu[0], rt, dn[1], up[1], f.coef);
             // raw inputs of line rho from the ring (an earlier hexad when PH < LAG*l)
             const int kb = PH - LAG * l;
-            const double *rb = kb >= 0 ? cur + (size_t)(kb >= 0 ? kb : 0) * BWP
-                                       : (kb >= -6 ? prev + (size_t)(kb >= -6 ? 6 + kb : 0) * BWP
-                                                   : prev2 + (size_t)(12 + kb >= 0 ? 12 + kb : 0) * BWP);
+            const int back = kb >= 0 ? 0 : (-kb + P - 1) / P;    // periods back (compile time after unrolling)
+            const double *rb = rbase[back] + (size_t)(kb + back * P) * BWP;
             auto rawget = [&](int a) -> double2 {
                 return *reinterpret_cast<const double2 *>(rb + (size_t)a * NR * BWP);
             };
@@ -326,7 +336,7 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
                 const bool rowin = LEAN || (rho >= g.row_lo && rho < g.row_hi);
                 const bool m0 = LEAN || (rowin & colin0), m1 = LEAN || (rowin & colin1);
                 const int sl_new = (PH - LAG * l + 24) % 3;     // line rho in U[l]
-                const int cs_new = (PH - LAG * l + 24) % 2;
+                const int cs_new = (PH - LAG * l + 24) % CCS;
                 U[l < L ? l : 0][sl_new][0] = m0 ? un[0] : 0.0;
                 U[l < L ? l : 0][sl_new][1] = m1 ? un[1] : 0.0;
 #pragma unroll
@@ -381,57 +391,52 @@ k_chain_tma(const C c_in, const ChainGeo g, const RedCtl rc, const __grid_consta
     using I3 = std::integral_constant<int, 3>;
     using I4 = std::integral_constant<int, 4>;
     using I5 = std::integral_constant<int, 5>;
-    int hs = 0;   // ring line of the current hexad
-    auto set_hexad = [&]() {
-        cur = tb + (size_t)hs * BWP;
-        prev = tb + (size_t)(hs == 0 ? NR - 6 : hs - 6) * BWP;
-        prev2 = NR >= 12 ? tb + (size_t)(hs >= 12 ? hs - 12 : hs + NR - 12) * BWP : tb;
+    int hs = 0;   // ring line of the current period
+    auto set_period = [&]() {
+#pragma unroll
+        for (int k = 0; k <= NB; ++k) {
+            int h = hs - k * P;
+            if (h < 0) h += NR;
+            rbase[k] = tb + (size_t)h * BWP;
+        }
+    };
+    // P phases with the given CHECK / LEAN flags
+    auto period = [&](auto chk, auto lean_c, const int t0) {
+        phase(I0{}, chk, lean_c, t0 + 0);
+        phase(I1{}, chk, lean_c, t0 + 1);
+        phase(I2{}, chk, lean_c, t0 + 2);
+        if (P == 6) {
+            phase(I3{}, chk, lean_c, t0 + 3);
+            phase(I4{}, chk, lean_c, t0 + 4);
+            phase(I5{}, chk, lean_c, t0 + 5);
+        }
     };
     if (C::LEAN) {
-        for (int t0 = 0; t0 < T; t0 += 6) {
-            set_hexad();
+        for (int t0 = 0; t0 < T; t0 += P) {
+            set_period();
 #ifdef KL_CHAIN_LEAN_ONLY      /* instruction counting only (scripts/sass_loops.py): drops the generic copy */
             if (true) {
 #else
-            if (lean_cta && t0 >= kLeanT0 && t0 + 6 <= T) {
+            if (lean_cta && t0 >= kLeanT0 && t0 + P <= T) {
 #endif
-                phase(I0{}, FF{}, LeanT{}, t0 + 0);
-                phase(I1{}, FF{}, LeanT{}, t0 + 1);
-                phase(I2{}, FF{}, LeanT{}, t0 + 2);
-                phase(I3{}, FF{}, LeanT{}, t0 + 3);
-                phase(I4{}, FF{}, LeanT{}, t0 + 4);
-                phase(I5{}, FF{}, LeanT{}, t0 + 5);
+                period(FF{}, LeanT{}, t0);
             } else {
-                phase(I0{}, TT{}, FF{}, t0 + 0);
-                phase(I1{}, TT{}, FF{}, t0 + 1);
-                phase(I2{}, TT{}, FF{}, t0 + 2);
-                phase(I3{}, TT{}, FF{}, t0 + 3);
-                phase(I4{}, TT{}, FF{}, t0 + 4);
-                phase(I5{}, TT{}, FF{}, t0 + 5);
+                period(TT{}, FF{}, t0);
             }
-            hs += 6;
+            hs += P;
             if (hs == NR) hs = 0;
         }
     } else {
         int t0 = 0;
-        for (; t0 + 6 <= T; t0 += 6) {
-            set_hexad();
-            phase(I0{}, FF{}, FF{}, t0 + 0);
-            phase(I1{}, FF{}, FF{}, t0 + 1);
-            phase(I2{}, FF{}, FF{}, t0 + 2);
-            phase(I3{}, FF{}, FF{}, t0 + 3);
-            phase(I4{}, FF{}, FF{}, t0 + 4);
-            phase(I5{}, FF{}, FF{}, t0 + 5);
-            hs += 6;
+        for (; t0 + P <= T; t0 += P) {
+            set_period();
+            period(FF{}, FF{}, t0);
+            hs += P;
             if (hs == NR) hs = 0;
         }
         if (t0 < T) {
-            set_hexad();
-            phase(I0{}, TT{}, FF{}, t0 + 0);
-            phase(I1{}, TT{}, FF{}, t0 + 1);
-            phase(I2{}, TT{}, FF{}, t0 + 2);
-            phase(I3{}, TT{}, FF{}, t0 + 3);
-            phase(I4{}, TT{}, FF{}, t0 + 4);
+            set_period();
+            period(TT{}, FF{}, t0);
         }
     }
 
