@@ -454,6 +454,7 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     const int RM = ts_rm(nc);
     size_t ntiles = (n + (size_t)kTsRB * RM - 1) / ((size_t)kTsRB * RM);
     int grid = (int)std::min<size_t>(ntiles, (size_t)kNumSM * 2);
+    if (c->opt_ts_blocks > 0 && c->opt_ts_blocks < grid) grid = c->opt_ts_blocks;
     const int hm = c->nranks == 1 ? h_mode : 0;
     const int *fl = gated ? c->d_I : nullptr;
     if (update)

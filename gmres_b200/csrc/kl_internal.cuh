@@ -134,6 +134,7 @@ struct kl_context_s {
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_tma = 1;
+    int opt_ts_blocks = 0;       // > 0: cap on the CTAs of the tall-skinny passes (tuning; env KL_TS_BLOCKS)
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
     int opt_stencil_rows = 0;   // 0: heuristic
@@ -381,14 +382,13 @@ __device__ __forceinline__ bool grid_sum(const double (&v)[K], const RedCtl &rc,
         const double *p = rc.partials + (size_t)k * kMaxBlocks;
         double a = 0.0;
         unsigned b = threadIdx.x;
-        for (; b + 7 * NT < nblocks; b += 8 * NT) {       // eight independent L2 loads in flight per thread
-            double t[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = __ldcg(p + b + q * NT);
+        for (; b < nblocks; b += 8 * NT) {       // eight independent L2 loads in flight per thread; the ragged last
+            double t[8];                        // round is predicated (adding +0.0 is exact), not a serial loop of
+#pragma unroll                                  // dependent L2 round trips (~0.7 us each under load)
+            for (int q = 0; q < 8; ++q) t[q] = (b + q * NT < nblocks) ? __ldcg(p + b + q * NT) : 0.0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) a += t[q];
         }
-        for (; b < nblocks; b += NT) a += __ldcg(p + b);
         s[k] = a;
     }
     block_sum<K, NT>(s, smem);

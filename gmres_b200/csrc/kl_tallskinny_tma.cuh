@@ -169,16 +169,37 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
     if (!s_last) return;
     __threadfence();
     const int ncr = nc + (tail0 >= 0 ? 1 : 0);
-    for (int col = wid; col < ncr; col += kTsWarps) {
-        const volatile double *pp = partials + (size_t)col * kTsMaxBlocks;
-        double sv = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) sv += pp[b];
-        sv = warp_sum(sv);
+    // column sums over the CTAs' partials, in CTA order.  All loads of two columns are issued before the first add
+    // (a lane owns at most kTsMaxPerLane partials of a column): the serial `sv += pp[b]` loop this replaces was a
+    // chain of dependent L2 round trips, 10 per column and 12 columns per warp at m = 95 -- most of the kernel's
+    // time on the L2-resident problems (C1: 300^2).
+    constexpr int kTsMaxPerLane = (kNumSM * 2 + 31) / 32;
+    for (int col0 = wid; col0 < ncr; col0 += 2 * kTsWarps) {
+        const int col1 = col0 + kTsWarps;
+        const double *p0 = partials + (size_t)col0 * kTsMaxBlocks;
+        const double *p1 = partials + (size_t)(col1 < ncr ? col1 : col0) * kTsMaxBlocks;
+        double t0[kTsMaxPerLane], t1[kTsMaxPerLane];
+#pragma unroll
+        for (int q = 0; q < kTsMaxPerLane; ++q) {
+            const unsigned b = lane + 32 * q;
+            t0[q] = b < gridDim.x ? __ldcg(p0 + b) : 0.0;
+            t1[q] = b < gridDim.x ? __ldcg(p1 + b) : 0.0;
+        }
+        double sv0 = 0.0, sv1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < kTsMaxPerLane; ++q) {
+            sv0 += t0[q];
+            sv1 += t1[q];
+        }
+        sv0 = warp_sum(sv0);
+        sv1 = warp_sum(sv1);
         if (lane == 0) {
-            out[col] = sv;
-            if (h_mode && col < nc) {
-                double *Hj = G.H + (size_t)j * G.ldh;
-                Hj[col] = (h_mode == 2) ? Hj[col] + sv : sv;
+            double *Hj = G.H + (size_t)j * G.ldh;
+            out[col0] = sv0;
+            if (h_mode && col0 < nc) Hj[col0] = (h_mode == 2) ? Hj[col0] + sv0 : sv0;
+            if (col1 < ncr) {
+                out[col1] = sv1;
+                if (h_mode && col1 < nc) Hj[col1] = (h_mode == 2) ? Hj[col1] + sv1 : sv1;
             }
         }
     }
