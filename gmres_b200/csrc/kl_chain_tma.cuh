@@ -464,7 +464,10 @@ inline bool chain_geometry(Ctx *c, int nx, int ny, ChainGeo *g, dim3 *grid, bool
     long rows = c->opt_stencil_rows > 0 ? c->opt_stencil_rows : ((L <= 3 || !single_input) ? 24 * L : 192);
     if (rows < 24) rows = 24;
     const long want = (long)kNumSM * 4;
-    while (rows > 12 * L && rows > 16 && gx * ((ny + rows - 1) / rows) < want) rows -= 6;
+    // small grids are launch-/latency-bound: many short marches (redundant lines are free there) beat few long ones
+    const long rmin = c->opt_chain_rows_min > 0 ? c->opt_chain_rows_min
+                                                : ((long)nx * ny <= (1L << 18) ? 6 : (12 * L > 16 ? 12 * L : 16));
+    while (rows - 6 >= rmin && gx * ((ny + rows - 1) / rows) < want) rows -= 6;
     if (rows > ny) rows = ny;
     long gy = (ny + rows - 1) / rows;
     if (gx * gy > kMaxBlocks) {

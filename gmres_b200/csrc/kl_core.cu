@@ -503,6 +503,8 @@ int kl_create(kl_handle_t *h, int device) {
     if (const char *e = getenv("KL_PERSISTENT")) c->opt_persistent = atoi(e) != 0;
     if (const char *e = getenv("KL_PERSIST_OCC")) c->opt_persist_occ = atoi(e);
     if (const char *e = getenv("KL_TS_BLOCKS")) c->opt_ts_blocks = atoi(e);
+    if (const char *e = getenv("KL_CHAIN_STEP_MIN")) c->opt_chain_step_min = atoll(e);
+    if (const char *e = getenv("KL_CHAIN_ROWS_MIN")) c->opt_chain_rows_min = atoi(e);
     if (const char *e = getenv("KL_STENCIL_ROWS")) c->opt_stencil_rows = atoi(e);
     if (const char *e = getenv("KL_PUSH_HALO")) c->opt_push_halo = atoi(e) != 0;
     if (const char *e = getenv("KL_INLINE_ALLREDUCE")) c->opt_inline_ar = atoi(e) != 0;

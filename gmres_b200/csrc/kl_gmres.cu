@@ -252,6 +252,8 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
        const double *__restrict__ h, const RedCtl rc, const int want_norm, const GmresDev G,
        const int j, const int fuse_givens, const int *__restrict__ flags) {
     // want_norm: bit 0 = reduce ||w||^2 ; bit 1 = selective mode: do nothing when I_SKIP3 is set
+    griddep_wait();
+    griddep_launch();
     if (flags && flags[I_CONV_AT] >= 0) return;
     if ((want_norm & 2) && flags[I_SKIP3]) return;
     extern __shared__ double sm[];   // max(ncols, 3*(m+2)) doubles + reduction scratch
@@ -458,11 +460,11 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     const int hm = c->nranks == 1 ? h_mode : 0;
     const int *fl = gated ? c->d_I : nullptr;
     if (update)
-        k_ts_tma<true><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                              out, G, j, hm, fl, tail0, tt);
+        KL_CUDA(c, launch_k(c, false, k_ts_tma<true>, dim3(grid), dim3(kTsThreads), smem, tm, w, n, nc, RM, h_in,
+                            c->d_partials, c->d_counter + 1, out, G, j, hm, fl, tail0, tt));
     else
-        k_ts_tma<false><<<grid, kTsThreads, smem, c->stream>>>(tm, w, n, nc, RM, h_in, c->d_partials, c->d_counter + 1,
-                                                               out, G, j, hm, fl, tail0, tt);
+        KL_CUDA(c, launch_k(c, false, k_ts_tma<false>, dim3(grid), dim3(kTsThreads), smem, tm, w, n, nc, RM, h_in,
+                            c->d_partials, c->d_counter + 1, out, G, j, hm, fl, tail0, tt));
     c->stats.kernel_launches++;
     if (c->nranks > 1) {
         KL_TRY(comm_allreduce(c, out, nc + (tail0 >= 0 ? 1 : 0)));
@@ -524,12 +526,13 @@ int launch_wmvh(Ctx *c, const double *V, size_t ldv, double *w, size_t n, int nc
     const int fuse = (givens && c->nranks == 1) ? 1 : 0;
     const int wn = (want_norm ? 1 : 0) | (honor_skip ? 2 : 0);
     RedCtl rc = redctl(c);
+    const int *fl = (gated || honor_skip) ? c->d_I : nullptr;
     if (vec == 2)
-        k_wmvh<2><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, wn, G, j, fuse,
-                                                         (gated || honor_skip) ? c->d_I : nullptr);
+        KL_CUDA(c, launch_k(c, false, k_wmvh<2>, dim3(grid), dim3(kTsThreads), smem, V, ldv, w, n, ncols, h, rc, wn, G, j,
+                            fuse, fl));
     else
-        k_wmvh<1><<<grid, kTsThreads, smem, c->stream>>>(V, ldv, w, n, ncols, h, rc, wn, G, j, fuse,
-                                                         (gated || honor_skip) ? c->d_I : nullptr);
+        KL_CUDA(c, launch_k(c, false, k_wmvh<1>, dim3(grid), dim3(kTsThreads), smem, V, ldv, w, n, ncols, h, rc, wn, G, j,
+                            fuse, fl));
     c->stats.kernel_launches++;
     if (want_norm && c->nranks > 1) {
         KL_TRY(comm_allreduce(c, c->d_S + S_RED, 1));
@@ -628,13 +631,17 @@ int gmres_mgsr_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x,
     // (large grids only: the temporally blocked kernel's CTAs are 240 columns x 48 lines, which is 14 CTAs at 300^2 --
     // there the two small stencil kernels, 76 CTAs each, are faster: 57 vs 61 us per step measured)
     const bool chain_step = fused && P.pc.kind == KL_PC_CBPR2 && chain_ok(&P, 2) &&
-                            (size_t)P.nx * (size_t)(P.ny / c->nranks) >= ((size_t)1 << 20);
+                            ((size_t)P.nx * (size_t)(P.ny / c->nranks) >= (size_t)c->opt_chain_step_min ||
+                             (c->nranks == 1 && (size_t)P.nx * (size_t)P.ny <= ((size_t)1 << 18)));   // launch-bound grids:
+                            // one launch less per step (300^2: 48.9 -> 44.3 us with 6-line marches); in between the
+                            // two stencil kernels fill the GPU better than the chain kernel's few CTAs
     const Cbpr2Coef cbc = chain_step ? cbpr2_coef(P.params) : Cbpr2Coef{1.0, 0.0};
     const bool coop = cgs2_coop_ok(c, n, ldv, m);
     // One restart cycle = a fixed sequence of launches (every pointer, column count and step index is known on
     // the host; convergence is a device-side gate), so it can be captured once and replayed as a CUDA graph:
     // at 300^2 (BASELINE config 1) a cycle is ~480 launches of 5-20 us kernels and launch overhead dominates.
     auto enqueue_cycle = [&]() -> int {
+        const PdlScope pdl_scope(c, c->nranks == 1);     // programmatic dependent launch for the whole cycle
         w = w_base;
         z = z_base;
         double *wn = w2;

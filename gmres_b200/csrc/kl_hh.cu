@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(kTsThreads)
 k_hh_apply_wy(const double *__restrict__ Y, const size_t ldv, const int nc, const double *__restrict__ t,
               const int src_mode, const long long row, const double *__restrict__ yv, double *dst,
               const int add_to_dst, const size_t n, const int *__restrict__ flags) {
+    griddep_wait();
+    griddep_launch();
     if (flags && flags[I_CONV_AT] >= 0) return;
     extern __shared__ double sh[];
     for (int c = threadIdx.x; c < nc; c += kTsThreads) sh[c] = t[c];
@@ -328,6 +330,8 @@ constexpr int kHhStepThreads = 1024;     // 32 warps: the O(j^2) triangular prod
 __global__ void __launch_bounds__(kHhStepThreads)
 k_hh_step_wy(const GmresDev G, const HhWy W, const double *w, const double *u, const int j, const int prec_variant) {
     extern __shared__ double sm[];     // 3*(m+2) for Givens + (m+2) for z
+    griddep_wait();
+    griddep_launch();
     if (G.I[I_CONV_AT] >= 0) return;
     constexpr int NW = kHhStepThreads / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -397,12 +401,14 @@ static int launch_apply_wy(Ctx *c, const double *Y, size_t ldv, int nc, const do
     size_t b = (n / vec + kTsThreads - 1) / kTsThreads;
     if (b > (size_t)kNumSM * 8) b = (size_t)kNumSM * 8;
     const size_t smem = sizeof(double) * (nc + 8);
+    const int *fl = gated ? c->d_I : nullptr;
+    const int addi = add;
     if (vec == 2)
-        k_hh_apply_wy<2><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
-                                                                 gated ? c->d_I : nullptr);
+        KL_CUDA(c, launch_k(c, false, k_hh_apply_wy<2>, dim3((unsigned)b), dim3(kTsThreads), smem, Y, ldv, nc, t, src_mode,
+                            row, yv, dst, addi, n, fl));
     else
-        k_hh_apply_wy<1><<<(int)b, kTsThreads, smem, c->stream>>>(Y, ldv, nc, t, src_mode, row, yv, dst, add, n,
-                                                                 gated ? c->d_I : nullptr);
+        KL_CUDA(c, launch_k(c, false, k_hh_apply_wy<1>, dim3((unsigned)b), dim3(kTsThreads), smem, Y, ldv, nc, t, src_mode,
+                            row, yv, dst, addi, n, fl));
     c->stats.kernel_launches++;
     return KL_OK;
 }
@@ -515,6 +521,7 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
     // captured once and replayed as a CUDA graph (KL_OPT_USE_GRAPH).  At 1024^2 (BASELINE config 2) a step is
     // 7 launches around ~250 us of work and the gaps between them were ~10 % of the step.
     auto enqueue_cycle = [&]() -> int {
+        const PdlScope pdl_scope(c, true);               // programmatic dependent launch (single GPU by construction)
         // g = 0 ; H = 0 (:241).  P = 0 is implicit: every reflector is fully written before use.
         KL_CUDA(c, cudaMemsetAsync(G.H, 0, sizeof(double) * (size_t)ldh * m, c->stream));
         KL_CUDA(c, cudaMemsetAsync(G.g, 0, sizeof(double) * (m + 2), c->stream));
@@ -557,7 +564,8 @@ int gmres_hh_solve(Ctx *c, const kl_operator_t *A, const double *b, double *x, i
                 // tvec was consumed by launch_apply_wy above and is refilled for the next step by k_hh_step_wy)
                 KL_TRY(launch_ts_tma(c, false, Pm, ldv, m + 1, w, n, nc, nullptr, W.svec, G, j, 0, true, -1, W.T, W.tvec, W.ldt));
                 KL_TRY(launch_ts_tma(c, true, Pm, ldv, m + 1, w, n, nc, W.tvec, G.hvec, G, j, 0, true, (long long)j + 2));
-                k_hh_step_wy<<<1, kHhStepThreads, sizeof(double) * 4 * (m + 2), c->stream>>>(G, W, w, G.hvec, j, prec_variant);
+                KL_CUDA(c, launch_k(c, false, k_hh_step_wy, dim3(1), dim3(kHhStepThreads), sizeof(double) * 4 * (m + 2), G, W,
+                                    (const double *)w, (const double *)G.hvec, j, prec_variant));
                 c->stats.kernel_launches += 1;
                 PHhNewReflector f;
                 set_gate(f, c, true, j, 1);

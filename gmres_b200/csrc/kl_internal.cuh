@@ -134,6 +134,9 @@ struct kl_context_s {
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_tma = 1;
+    int pdl_scope = 0;           // > 0: every PDL-capable launch uses programmatic dependent launch (PdlScope)
+    long long opt_chain_step_min = 1 << 20;   // one-pass GMRES step (ChGmresStep) from this many local unknowns on (env KL_CHAIN_STEP_MIN)
+    int opt_chain_rows_min = 0;  // > 0: lower bound of the chain kernels' lines per CTA on small grids (env KL_CHAIN_ROWS_MIN)
     int opt_ts_blocks = 0;       // > 0: cap on the CTAs of the tall-skinny passes (tuning; env KL_TS_BLOCKS)
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
     int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
@@ -455,6 +458,7 @@ __device__ __noinline__ void peer_allreduce_block(const RedCtl &rc) {
 // no-ops for kernels launched the ordinary way.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 
 // ------------------------------------------------------------------------
 // 5-point operator arithmetic.  OPK selects the reference's rounding order.
@@ -782,6 +786,34 @@ static __global__ void k_post(const PostAny post, const int *flags, const int st
 // launch helpers (host)
 // ------------------------------------------------------------------------
 inline RedCtl redctl(Ctx *c) { return RedCtl{c->d_partials, c->d_counter, c->d_S + S_RED, nullptr, c->d_I}; }
+
+// Launch with or without the programmatic-stream-serialisation attribute.  ONLY for kernels that execute
+// griddep_wait() before they read anything a predecessor wrote AND before any early exit (a grid that returns
+// without waiting would let its successor overtake the grid before it).  Inside a PdlScope (a solver's step loop on
+// one GPU) every such launch overlaps its launch latency, CTA scheduling and barrier set-up with the predecessor's
+// tail: on the L2-resident problems (C1, 300^2) an Arnoldi step is five dependent ~5 us kernels and the launch gaps
+// were a third of it.
+struct PdlScope {
+    Ctx *c;
+    bool on;
+    PdlScope(Ctx *c_, bool on_) : c(c_), on(on_) { if (on) ++c->pdl_scope; }
+    ~PdlScope() { if (on) --c->pdl_scope; }
+};
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(Ctx *c, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            Args &&...args) {
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = ((pdl || c->pdl_scope > 0) && c->opt_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 // Reducing kernel on several GPUs with NVLink peer memory: the kernel's last block does the all-reduce and runs
 // the post functor itself.  Returns true when that path is taken (then finish_reduction must not be called).
 inline bool redctl_inline_allreduce(Ctx *c, RedCtl &rc, int nred) {
@@ -915,7 +947,7 @@ inline int launch_stencil(Ctx *c, const kl_operator_t *op, F f, int nx, int ny, 
     cfg.blockDim = dim3(kStencilThreads);
     cfg.stream = c->stream;
     cfg.attrs = at;
-    cfg.numAttrs = (pdl && c->opt_pdl) ? 1 : 0;
+    cfg.numAttrs = ((pdl || c->pdl_scope > 0) && c->opt_pdl) ? 1 : 0;
     // the opt-in for > 48 KB of dynamic shared memory and the occupancy are per device (a process may hold
     // handles on several devices)
 #define KL_ST_GEO(KERNEL, SMEM) KL_ST_GEO2(KERNEL, SMEM, false)
@@ -988,9 +1020,9 @@ inline int launch_pointwise(Ctx *c, F f, size_t n, const Post &post) {
     const int fuse = c->nranks == 1 || inl;
     const PostAny pa = to_any(post);
     if (n % 2 == 0)
-        k_pointwise<F, 2><<<pw_grid(n / 2), kPwThreads, 0, c->stream>>>(f, n, rc, pa, fuse);
+        KL_CUDA(c, launch_k(c, false, k_pointwise<F, 2>, dim3(pw_grid(n / 2)), dim3(kPwThreads), 0, f, n, rc, pa, fuse));
     else
-        k_pointwise<F, 1><<<pw_grid(n), kPwThreads, 0, c->stream>>>(f, n, rc, pa, fuse);
+        KL_CUDA(c, launch_k(c, false, k_pointwise<F, 1>, dim3(pw_grid(n)), dim3(kPwThreads), 0, f, n, rc, pa, fuse));
     c->stats.kernel_launches++;
     if (F::NRED > 0 && !inl) return finish_reduction(c, F::NRED, post, f.flags, f.step, f.run_on_conv);
     return KL_OK;

@@ -217,6 +217,8 @@ k_ts_tma(const __grid_constant__ CUtensorMap tmV, double *w, const size_t n, con
          double *__restrict__ out, const GmresDev G, const int j, const int h_mode,
          const int *__restrict__ flags, const long long tail0 /* >= 0: out[nc] = sum_{row >= tail0} w_row^2 */,
          const TsTail tt) {
+    griddep_wait();      // before the gate: flags, w, h_in and the newest column of V come from the predecessors
+    griddep_launch();
     if (flags && flags[I_CONV_AT] >= 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ts_pass<UPDATE>(tmV, w, n, nc, RM, h_in, partials, counter, out, G, j, h_mode, tail0, tt, smem_raw);

@@ -131,7 +131,7 @@ def test_cg_operator_twice_matches_stored_ap(kl, h, nx, ny):
     assert np.abs(g.x - 1).max() < 1e-7 and np.abs(g.x - s.x).max() < 1e-9
 
 
-@pytest.mark.parametrize("nx,ny,m", [(1024, 1024, 30), (2048, 640, 20), (1200, 1000, 24)])
+@pytest.mark.parametrize("nx,ny,m", [(1024, 1024, 30), (2048, 640, 20), (1200, 1000, 24), (300, 300, 50), (130, 76, 12), (512, 500, 24)])
 def test_gmres_one_pass_step_bit_identical_to_two_kernels(kl, h, nx, ny, m):
     """GMRES-MGSR + cbpr2: V_j = w/h, z = A V_j and w = cbpr2(z) as ONE temporally blocked pass (ChGmresStep,
     kl_gmres.cu) against the two separate kernels (KL_OPT_CHAIN = 0).  Every point sees the same divisions and the
