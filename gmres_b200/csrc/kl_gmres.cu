@@ -269,15 +269,18 @@ k_wmvh(const double *__restrict__ V, const size_t ldv, double *w, const size_t n
 __global__ void __launch_bounds__(kTsThreads, 2)
 k_cgs2_coop(const __grid_constant__ CUtensorMap tmV, const double *__restrict__ V, const size_t ldv, double *w,
             const size_t n, const int nc, const int RM, double *__restrict__ partials, unsigned int *counter,
-            const RedCtl rc, const GmresDev G, const int j, const int *__restrict__ flags) {
+            const RedCtl rc, const GmresDev G, const int j, const int *__restrict__ flags, unsigned int *sync_flag) {
     if (flags && flags[I_CONV_AT] >= 0) return;          // grid-uniform: every CTA leaves before the first barrier
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    // Grid barriers without cooperative_groups: a pass already ends with "every CTA arrives at a counter, the last one
+    // sums the partials"; the other CTAs only have to wait for that block's result, so the barrier is the arrival
+    // plus one release / acquire flag (its value read here, before any CTA can have arrived anywhere, + the pass
+    // number).  The cooperative launch is kept for its co-residency guarantee.
+    unsigned f0;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f0) : "l"(sync_flag) : "memory");
     const TsTail none{nullptr, nullptr, 0};
-    ts_pass<false>(tmV, w, n, nc, RM, nullptr, partials, counter, G.hvec, G, j, 1, -1, none, smem_raw);
-    grid.sync();
-    ts_pass<true>(tmV, w, n, nc, RM, G.hvec, partials, counter, G.hvec2, G, j, 2, -1, none, smem_raw);
-    grid.sync();
+    ts_pass<false>(tmV, w, n, nc, RM, nullptr, partials, counter, G.hvec, G, j, 1, -1, none, smem_raw, sync_flag, f0 + 1u);
+    ts_pass<true>(tmV, w, n, nc, RM, G.hvec, partials, counter, G.hvec2, G, j, 2, -1, none, smem_raw, sync_flag, f0 + 2u);
     wmvh_pass<2>(V, ldv, w, n, nc, G.hvec2, rc, 1, G, j, 1, reinterpret_cast<double *>(smem_raw));
 }
 
@@ -513,7 +516,8 @@ int launch_cgs2_coop(Ctx *c, const double *V, size_t ldv, int ncols_total, doubl
     cfg.stream = c->stream;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_cgs2_coop, tm, Vc, ldv_, w, n_, nc, RM, partials, counter, rc, G, j, fl));
+    unsigned int *sync_flag = c->d_counter + 8;
+    KL_CUDA(c, cudaLaunchKernelEx(&cfg, k_cgs2_coop, tm, Vc, ldv_, w, n_, nc, RM, partials, counter, rc, G, j, fl, sync_flag));
     c->stats.kernel_launches++;
     return KL_OK;
 }

@@ -145,8 +145,10 @@ struct kl_context_s {
                                  // than one CTA per tile (static tile assignment balances worse than the hardware's
                                  // dynamic CTA scheduling, profiles/r02_cta_timeline_persistent.txt): off by default
     int opt_persist_occ = 0;     // CTAs per SM of the persistent grid (0 = full occupancy)
-    int opt_coop = 0;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP): measured 4 % SLOWER than
-                                 // three graph-replayed launches at 300^2 (fewer co-resident CTAs, two grid barriers): off
+    int opt_coop = 0;            // cooperative one-kernel CGS2 step on small grids (KL_OPT_COOP).  Measured at 300^2 against
+                                 // three graph-replayed launches: 4 % slower with cooperative_groups grid barriers, 1.6 %
+                                 // faster (43.5 vs 44.2 us per step) with the arrival-counter + flag barriers it has now:
+                                 // the step is bound by what happens INSIDE a pass, not by launches.  Off.
     int opt_reverse = 0;         // K2-type kernels march against their predecessor's direction (KL_OPT_REVERSE): no
                                  // measurable L2 reuse on B200 (264.0 vs 265.0 us at 8 GPUs): off by default
     int opt_stencil_stagger = 0; // staggered tile heights (KL_OPT_STENCIL_STAGGER): measured neutral, off by default

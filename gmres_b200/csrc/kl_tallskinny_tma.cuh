@@ -47,7 +47,8 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
                                         const double *__restrict__ h_in, double *__restrict__ partials,
                                         unsigned int *counter, double *__restrict__ out, const GmresDev &G, const int j,
                                         const int h_mode, const long long tail0, const TsTail &tt,
-                                        unsigned char *smem_raw) {
+                                        unsigned char *smem_raw, unsigned int *sync_flag = nullptr,
+                                        const unsigned sync_target = 0u) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int RB = kTsRB * RM;                                  // rows per tile
     const int nslice = kTsWarps / RM;                            // column slices
@@ -166,7 +167,20 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
         s_last = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) {
+        // persistent use (k_cgs2_coop): wait until the last block has published the column sums.  The arrival above
+        // and this flag together are the grid barrier -- no second barrier after the reduction.
+        if (sync_flag) {
+            if (threadIdx.x == 0) {
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync_flag) : "memory");
+                } while ((int)(v - sync_target) < 0);
+            }
+            __syncthreads();
+        }
+        return;
+    }
     __threadfence();
     const int ncr = nc + (tail0 >= 0 ? 1 : 0);
     // column sums over the CTAs' partials, in CTA order.  All loads of two columns are issued before the first add
@@ -207,6 +221,13 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
     if (!UPDATE && tt.T) {
         __syncthreads();          // out[] was written by this block's warps
         ts_tail_tT(tt, out, nc);
+    }
+    if (sync_flag) {
+        __syncthreads();          // every warp's column sums (and the counter reset) are written
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sync_flag), "r"(sync_target) : "memory");
+        }
     }
 }
 
