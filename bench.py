@@ -44,7 +44,7 @@ WORKLOADS = {
     "cg16384": dict(solver="cg_omp", nx=16384, ny=16384, scaling="strong", pc=None, m=0),
     "pcg16384": dict(solver="pcg_omp", nx=16384, ny=16384, scaling="strong", pc="cbpr2", m=0),
     "gmres4096": dict(solver="gmres_mgsr_omp", nx=4096, ny=4096, scaling="strong", pc="cbpr2", m=95),
-    "gmres4096sel": dict(solver="gmres_mgsr_omp", nx=4096, ny=4096, scaling="strong", pc="cbpr2", m=95, ortho=2, eta=100),
+    "gmres4096sel": dict(solver="gmres_mgsr_omp", nx=4096, ny=4096, scaling="strong", pc="cbpr2", m=95, ortho=2, eta=300),
     "hh1024": dict(solver="gmres_hh_omp", nx=1024, ny=1024, scaling="strong", pc=None, m=95),
     "bicgstab8192": dict(solver="pbicgstab_omp", nx=8192, ny=8192, scaling="weak", pc="cbpr2", m=0,
                          aniso=(1.0, 0.01)),
@@ -182,12 +182,12 @@ def run_gpu_solver(kl, h, w, b, nx, ny, iters, profile=False):
     h.set_option(2, cycles)   # KL_OPT_MAX_RESTARTS
     if s == "gmres_mgsr_omp":
         h.set_ortho(w.get("ortho", 1))
-        h.set_option(11, w.get("eta", 707))   # KL_OPT_REORTH_ETA (selective mode only)
+        h.set_option(11, w.get("eta", 300))   # KL_OPT_REORTH_ETA (selective mode only)
         try:
             return h.gmres_mgsr_omp(A, b, m, 0.0, M, P_REF, nx=nx, ny=ny)
         finally:
             h.set_ortho(1)
-            h.set_option(11, 707)
+            h.set_option(11, 300)
     if s == "gmres_hh_omp":
         return h.gmres_hh_omp(A, b, m, 0.0, nx=nx, ny=ny)
     raise ValueError(s)

@@ -139,7 +139,9 @@ struct kl_context_s {
     int opt_chain_rows_min = 0;  // > 0: lower bound of the chain kernels' lines per CTA on small grids (env KL_CHAIN_ROWS_MIN)
     int opt_ts_blocks = 0;       // > 0: cap on the CTAs of the tall-skinny passes (tuning; env KL_TS_BLOCKS)
     int opt_chain = 1;          // temporally blocked (chained) stencil kernels, kl_chain_tma.cuh
-    int opt_reorth_eta_permille = 707;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w|| (1/sqrt 2: Kahan-Parlett)
+    int opt_reorth_eta_permille = 300;   // KL_ORTHO_CGS2_SELECTIVE: reorthogonalise iff ||w'|| < eta ||w||.  0.3 from the sweep in
+                                         // profiles/r02_eta_sweep.json (identical iteration counts for every eta <= 0.707 on
+                                         // 1024^2..4096^2, ||I - V^T V|| <= 2e-12); 707 = 1/sqrt 2 is Kahan-Parlett's bound
     int opt_stencil_rows = 0;   // 0: heuristic
     int opt_persistent = 0;      // persistent CTAs in the TMA stencil kernels (KL_OPT_PERSISTENT): measured 4-8 % slower
                                  // than one CTA per tile (static tile assignment balances worse than the hardware's

@@ -125,7 +125,7 @@ enum {
     KL_OPT_FUSE = 7,          /* 1 (default): fused kernels; 0: one kernel per reference loop */
     KL_OPT_PROFILE = 8,       /* 1: CUDA-event pairs around every hot kernel (kl_get_profile)  */
     KL_OPT_TMA = 9,           /* 1 (default): TMA-staged stencil kernels; 0: register-pipelined ones */
-    KL_OPT_REORTH_ETA = 11,   /* KL_ORTHO_CGS2_SELECTIVE threshold eta in 1/1000 (default 707 = 1/sqrt2):
+    KL_OPT_REORTH_ETA = 11,   /* KL_ORTHO_CGS2_SELECTIVE threshold eta in 1/1000 (default 300; 707 = 1/sqrt2 is the classical bound):
                                  the second Gram-Schmidt pass runs only when ||w'|| < eta ||w||          */
     KL_OPT_CHAIN = 12,        /* 1 (default): temporally blocked kernels -- several dependent operator applications
                                  (Chebyshev degree k, cbpr2 o A, A o cbpr2) in one pass over HBM; 0: one pass each */

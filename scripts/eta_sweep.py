@@ -28,6 +28,6 @@ for ns in [int(a) for a in sys.argv[1:]] or [1024, 2048]:
     out[str(ns)] = rows
     del b
     torch.cuda.empty_cache()
-h.set_ortho(1); h.set_option(11, 707)
+h.set_ortho(1); h.set_option(11, 300)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/r2_eta_sweep.json", "w"), indent=1)

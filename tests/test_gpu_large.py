@@ -200,7 +200,7 @@ def test_gmres_selective_fast_mode_4096(env):
         s = h.gmres_mgsr_omp(kl.stvec, b, m, 0.0, kl.cbpr2, P, nx=n, ny=n)
     finally:
         h.set_ortho(1)
-        h.set_option(11, 707)
+        h.set_option(11, 300)
         h.set_option(3, 0)
         h.set_option(2, 1000)
     print(f"selective eta=0.3 4096^2: skipped {s.stats['reorth_skipped']} of {m}, history rel {hist_rel(s.history, a.history):.2e}, "

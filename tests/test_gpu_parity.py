@@ -455,11 +455,12 @@ def test_gmres_selective_reorthogonalisation(kl, h, ko, ns, m):
     oi = _its(o, m)
     h.set_ortho(2)
     try:
+        h.set_option(11, 707)     # eta = 1/sqrt 2 (Kahan-Parlett); the default is 0.3
         g = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
         h.set_option(11, 100)     # eta = 0.1
         g1 = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-8, kl.cbpr2, P)
     finally:
-        h.set_option(11, 707)
+        h.set_option(11, 300)
         h.set_ortho(1)
     for tag, r in (("eta=0.707", g), ("eta=0.1", g1)):
         print(f"selective ns={ns} {tag}: its {_its(r, m)} (oracle {oi}), skipped {r.stats['reorth_skipped']} of "
