@@ -512,7 +512,7 @@ int kl_create(kl_handle_t *h, int device) {
     ok = ok && cudaMalloc(&c->d_S, sizeof(double) * S_COUNT) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_I, sizeof(int) * I_COUNT) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_partials, sizeof(double) * std::max((size_t)kMaxCols * 1024, (size_t)kMaxRed * kMaxBlocks)) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_counter, sizeof(unsigned) * 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_counter, sizeof(unsigned) * 128) == cudaSuccess;
     c->hist_cap = 1 << 20;
     ok = ok && cudaMalloc(&c->d_hist, sizeof(double) * c->hist_cap) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_pinned, sizeof(double) * S_COUNT) == cudaSuccess;
@@ -522,7 +522,7 @@ int kl_create(kl_handle_t *h, int device) {
     if (ok) {
         ok = cudaMemset(c->d_S, 0, sizeof(double) * S_COUNT) == cudaSuccess &&
              cudaMemset(c->d_I, 0, sizeof(int) * I_COUNT) == cudaSuccess &&
-             cudaMemset(c->d_counter, 0, sizeof(unsigned) * 16) == cudaSuccess;
+             cudaMemset(c->d_counter, 0, sizeof(unsigned) * 128) == cudaSuccess;
     }
     if (!ok) {
         cudaGetLastError();

@@ -479,6 +479,12 @@ int launch_ts_tma(Ctx *c, bool update, const double *V, size_t ldv, int ncols_to
     return KL_OK;
 }
 
+#ifdef KL_TRACE
+extern "C" int kl_debug_trace_ts(unsigned long long *out, int n) {
+    return cudaMemcpyFromSymbol(out, g_trace_ts, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 // cooperative CGS2 step (see k_cgs2_coop): single GPU, TMA path, problems small enough to be launch-bound
 bool cgs2_coop_ok(Ctx *c, size_t n, size_t ldv, int m) {
     return c->nranks == 1 && c->opt_coop && !c->opt_profile && c->opt_ortho == KL_ORTHO_CGS2 &&

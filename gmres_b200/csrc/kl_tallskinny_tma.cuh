@@ -40,6 +40,20 @@ static __device__ __noinline__ void ts_tail_tT(const TsTail tt, const double *s,
     }
 }
 
+constexpr int kTsLd = 128;                 // doubles per row of partial sums (m + 2 <= 128)
+constexpr int kTsGroup = 16;               // CTAs per first-level reduction group (296 CTAs -> 19 groups: one round each level)
+constexpr int kTsGroupRow = 512;           // rows kTsGroupRow.. of the partials hold the group sums (grid <= 512 CTAs)
+constexpr int kTsGroupCounterOffset = 15;  // group arrival counters: counter[15 .. 15 + 64) (counter = Ctx::d_counter + 1)
+
+#ifdef KL_TRACE
+// debug build only: per-CTA time stamps of the last tall-skinny pass of this translation unit
+//   [0] entry  [1] first tile landed  [2] tile loop done  [3] arrived at the grid counter  [4] (last block) sums written
+static __device__ unsigned long long g_trace_ts[8 * 512];
+#define KL_TS_STAMP(k) if (threadIdx.x == 0 && blockIdx.x < 512) g_trace_ts[8 * blockIdx.x + (k)] = gtimer();
+#else
+#define KL_TS_STAMP(k)
+#endif
+
 // one tall-skinny pass by the whole grid (body of k_ts_tma; also called three times in a row, with grid-wide
 // barriers in between, by the cooperative kernel k_cgs2_coop in kl_gmres.cu)
 template <bool UPDATE>
@@ -49,6 +63,7 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
                                         const int h_mode, const long long tail0, const TsTail &tt,
                                         unsigned char *smem_raw, unsigned int *sync_flag = nullptr,
                                         const unsigned sync_target = 0u) {
+    KL_TS_STAMP(0)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int RB = kTsRB * RM;                                  // rows per tile
     const int nslice = kTsWarps / RM;                            // column slices
@@ -109,6 +124,9 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
             wnext = (k + 1 < my_tiles && rn < n) ? w[rn] : 0.0;
         }
         mbar_wait(&full[s], (unsigned)((k / kTsNst) & 1));
+#ifdef KL_TRACE
+        if (k == 0) { KL_TS_STAMP(1) }
+#endif
         const double *tile = reinterpret_cast<const double *>(reinterpret_cast<unsigned char *>(tiles) +
                                                                (size_t)s * tile_stride);
         double v[kTsCpw];
@@ -135,6 +153,7 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
             issue(blockIdx.x + (k + kTsNst) * gridDim.x, s);
         }
     }
+    KL_TS_STAMP(2)
     // ---- block stage: reduce over the 32 row-lanes, then over the RM row groups
 #pragma unroll
     for (int c = 0; c < kTsCpw; ++c) {
@@ -142,11 +161,13 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
         if (lane == 0) s_red[(rowgrp * 8 + slice) * kTsCpw + c] = sv;
     }
     __syncthreads();
+    // partial sums: one row of kTsLd doubles per CTA (column-contiguous: the writes below and the one-thread-per-column
+    // sums of the grid stage are coalesced)
     if (threadIdx.x < nc) {
         const int sl = threadIdx.x / kTsCpw, cc = threadIdx.x % kTsCpw;
         double sv = 0.0;
         for (int q = 0; q < RM; ++q) sv += s_red[(q * 8 + sl) * kTsCpw + cc];
-        partials[(size_t)threadIdx.x * kTsMaxBlocks + blockIdx.x] = sv;
+        partials[(size_t)blockIdx.x * kTsLd + threadIdx.x] = sv;
     }
     if (tail0 >= 0) {
         __syncthreads();
@@ -156,20 +177,21 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int q = 0; q < kTsWarps; ++q) t += s_red[q];
-            partials[(size_t)nc * kTsMaxBlocks + blockIdx.x] = t;
+            partials[(size_t)blockIdx.x * kTsLd + nc] = t;
         }
     }
-    // ---- grid stage (same as k_vtw)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned prev = atomicAdd(counter, 1u);
-        s_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) {
-        // persistent use (k_cgs2_coop): wait until the last block has published the column sums.  The arrival above
-        // and this flag together are the grid barrier -- no second barrier after the reduction.
+    // ---- grid stage, two levels, fixed order (same launch configuration => same bits).  Level 1: the CTAs form groups
+    // of kTsGroup consecutive block ids; the last CTA of a group to arrive adds the group's partials (one thread per
+    // column, all loads in flight) -- this runs while other groups are still streaming.  Level 2: the last group to
+    // finish adds the <= 19 group sums the same way.  The flat version (one warp per column pair, lanes over the 296
+    // CTAs) took 6 us at m = 95: six serial rounds of L2 latency, a third of the whole pass on L2-resident bases.
+    const int ncr = nc + (tail0 >= 0 ? 1 : 0);
+    const unsigned grp = blockIdx.x / kTsGroup, ngrp = (gridDim.x + kTsGroup - 1) / kTsGroup;
+    const unsigned gsize = min((unsigned)kTsGroup, gridDim.x - grp * kTsGroup);
+    unsigned int *gcounter = counter + kTsGroupCounterOffset;
+    auto wait_result = [&]() {
+        // persistent use (k_cgs2_coop): wait until the last block has published the column sums.  The arrivals and
+        // this flag together are the grid barrier -- no second barrier after the reduction.
         if (sync_flag) {
             if (threadIdx.x == 0) {
                 unsigned v;
@@ -179,45 +201,63 @@ __device__ __forceinline__ void ts_pass(const CUtensorMap &tmV, double *w, const
             }
             __syncthreads();
         }
+    };
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned prev = atomicAdd(gcounter + grp, 1u);
+        s_last = (prev == gsize - 1);
+        KL_TS_STAMP(3)
+    }
+    __syncthreads();
+    if (!s_last) {
+        wait_result();
         return;
     }
     __threadfence();
-    const int ncr = nc + (tail0 >= 0 ? 1 : 0);
-    // column sums over the CTAs' partials, in CTA order.  All loads of two columns are issued before the first add
-    // (a lane owns at most kTsMaxPerLane partials of a column): the serial `sv += pp[b]` loop this replaces was a
-    // chain of dependent L2 round trips, 10 per column and 12 columns per warp at m = 95 -- most of the kernel's
-    // time on the L2-resident problems (C1: 300^2).
-    constexpr int kTsMaxPerLane = (kNumSM * 2 + 31) / 32;
-    for (int col0 = wid; col0 < ncr; col0 += 2 * kTsWarps) {
-        const int col1 = col0 + kTsWarps;
-        const double *p0 = partials + (size_t)col0 * kTsMaxBlocks;
-        const double *p1 = partials + (size_t)(col1 < ncr ? col1 : col0) * kTsMaxBlocks;
-        double t0[kTsMaxPerLane], t1[kTsMaxPerLane];
+    if ((int)threadIdx.x < ncr) {
+        const double *pp = partials + (size_t)grp * kTsGroup * kTsLd + threadIdx.x;
+        double t[kTsGroup];
 #pragma unroll
-        for (int q = 0; q < kTsMaxPerLane; ++q) {
-            const unsigned b = lane + 32 * q;
-            t0[q] = b < gridDim.x ? __ldcg(p0 + b) : 0.0;
-            t1[q] = b < gridDim.x ? __ldcg(p1 + b) : 0.0;
-        }
-        double sv0 = 0.0, sv1 = 0.0;
+        for (int q = 0; q < kTsGroup; ++q) t[q] = (unsigned)q < gsize ? __ldcg(pp + (size_t)q * kTsLd) : 0.0;
+        double sv = 0.0;
 #pragma unroll
-        for (int q = 0; q < kTsMaxPerLane; ++q) {
-            sv0 += t0[q];
-            sv1 += t1[q];
+        for (int q = 0; q < kTsGroup; ++q) sv += t[q];
+        partials[(size_t)(kTsGroupRow + grp) * kTsLd + threadIdx.x] = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gcounter[grp] = 0u;
+        __threadfence();
+        unsigned prev = atomicAdd(counter, 1u);
+        s_last = (prev == ngrp - 1);
+    }
+    __syncthreads();
+    if (!s_last) {
+        wait_result();
+        return;
+    }
+    __threadfence();
+    if ((int)threadIdx.x < ncr) {
+        const double *pp = partials + (size_t)kTsGroupRow * kTsLd + threadIdx.x;
+        double sv = 0.0;
+        for (unsigned g0 = 0; g0 < ngrp; g0 += 20) {        // <= 19 groups at 296 CTAs: one round of loads in flight
+            double t[20];
+#pragma unroll
+            for (int q = 0; q < 20; ++q) t[q] = g0 + q < ngrp ? __ldcg(pp + (size_t)(g0 + q) * kTsLd) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 20; ++q) sv += t[q];
         }
-        sv0 = warp_sum(sv0);
-        sv1 = warp_sum(sv1);
-        if (lane == 0) {
+        const int col = threadIdx.x;
+        out[col] = sv;
+        if (h_mode && col < nc) {
             double *Hj = G.H + (size_t)j * G.ldh;
-            out[col0] = sv0;
-            if (h_mode && col0 < nc) Hj[col0] = (h_mode == 2) ? Hj[col0] + sv0 : sv0;
-            if (col1 < ncr) {
-                out[col1] = sv1;
-                if (h_mode && col1 < nc) Hj[col1] = (h_mode == 2) ? Hj[col1] + sv1 : sv1;
-            }
+            Hj[col] = (h_mode == 2) ? Hj[col] + sv : sv;
         }
     }
+    __syncthreads();
     if (threadIdx.x == 0) *counter = 0u;
+    KL_TS_STAMP(4)
     if (!UPDATE && tt.T) {
         __syncthreads();          // out[] was written by this block's warps
         ts_tail_tT(tt, out, nc);
