@@ -180,10 +180,28 @@ def main():
         C[f"hilbert_{n}"] = dict(n=n, H=lst(Hm))
 
     # ---- the reference's own driver program, tests/test_poisson_mf.f90 (argv = grid size, restart length) -------------
-    for argv in (("16", "10"), ("24", "20")):
+    # ("100", "95"): the reference's own restart length and tolerance (README.md:20 runs 300 95; 300^2 takes hours in the
+    # interpreter, 100^2 takes 100 s)
+    for argv in (("16", "10"), ("24", "20")) + (() if args.quick else (("100", "95"),)):
         out = w.run_program("test_poisson_mf", argv)
-        C["program_test_poisson_mf_" + "_".join(argv)] = dict(
+        rec = dict(
             argv=list(argv), records=[r["items"] for r in out if r["items"] and not str(r["items"][0]).startswith("Elapsed")])
+        if argv == ("100", "95"):
+            # the second cycle of a tol = 1e-15 solve starts from a residual at the rounding level of x and is not
+            # reproducible (see the note): keep the first-cycle histories of both solvers as the pinned quantity
+            ns_, m_ = int(argv[0]), int(argv[1])
+            for module, name, capvar, key in (("gmres_hh_mod", "gmres_hh_prec_omp", "stages", "hh_prec_cycle1_final_err"),
+                                              ("gmres_mgsr_mod", "gmres_mgsr_omp", "max_restarts", "mgsr_cycle1_final_err")):
+                default_cap = w.ns[module][capvar]
+                w.ns[module][capvar] = 1
+                r1 = call(module, name, ax_vec=stvec, b=rhs(ns_), m=m_, tol=1e-15, m_inv=cbpr2, params=params)
+                w.ns[module][capvar] = default_cap
+                rec[key] = lst(r1["final_err"])
+            rec["note"] = ("first-cycle histories (restart cap 1) of gmres_hh_prec_omp / gmres_mgsr_omp at the driver's tol 1e-15; "
+                           "the second cycle starts from a residual at the rounding level of x (1.3e-9 relative), so its length "
+                           "is not reproducible (reference 54 iterations, the C oracle 72 from an initial residual that differs "
+                           "by 6e-8 relative)")
+        C["program_test_poisson_mf_" + "_".join(argv)] = rec
 
     G["seconds_total"] = round(time.time() - t_all, 1)
     with open(args.out, "w") as f:

@@ -169,6 +169,16 @@ def test_driver_program_numbers(kl, h, ref):
         b = rhs(kl, h, ns)
         hh = h.gmres_hh_prec_omp(kl.stvec, b, m, 1e-15, kl.cbpr2, P)       # test_poisson_mf.f90:45
         mg = h.gmres_mgsr_omp(kl.stvec, b, m, 1e-15, kl.cbpr2, P)          # :76
-        for g, r_it, r_l in ((hh, its[0], lmax[0]), (mg, its[1], lmax[1])):
-            assert abs(((g.restart_out - 1) * m + g.n_out) - r_it[1]) <= 1, key
+        for g, r_it, r_l, ck in ((hh, its[0], lmax[0], "hh_prec_cycle1_final_err"), (mg, its[1], lmax[1], "mgsr_cycle1_final_err")):
+            g_it = (g.restart_out - 1) * m + g.n_out
+            if r_it[3] == 1 or ck not in c:
+                assert abs(g_it - r_it[1]) <= 1, key
+            else:
+                # several cycles at tol 1e-15 (the 100 x 95 run): the first cycle is the reproducible part (1e-10
+                # against the reference's own first-cycle history); the later cycles start from a residual at the
+                # rounding level of x and their length is not reproducible even between two runs of the reference
+                # (see the fixture's note and tests/test_reference_golden.py)
+                assert abs(g_it - r_it[1]) <= 0.2 * r_it[1], (key, g_it, r_it)
+                assert hist_rel(g.history[:m], np.array(c[ck]), 1e-9) < 1e-10, (key, ck)
+            assert abs(g.restart_out - r_it[3]) <= 1, key
             assert np.max(np.abs(g.x - 1.0)) < 10 * max(r_l[1], 1e-14), key

@@ -160,8 +160,17 @@ def test_driver_program_output_matches(ko, ref):
         b = ko.manufactured_rhs(ko.stvec_fn(), ns)
         hh = ko.gmres_hh(ko.stvec_fn(), b, m, 1e-15, ko.cbpr2_fn(), P_REF)        # test_poisson_mf.f90:45
         mg = ko.gmres_mgsr_omp(ko.stvec_fn(), b, m, 1e-15, ko.cbpr2_fn(), P_REF)  # :76
-        for o, r_it, r_l in ((hh, its[0], lmax[0]), (mg, its[1], lmax[1])):
-            assert abs(((o.restart_out - 1) * m + o.n_out) - r_it[1]) <= 1, key     # tol 1e-15: +-1
+        for o, r_it, r_l, ck in ((hh, its[0], lmax[0], "hh_prec_cycle1_final_err"), (mg, its[1], lmax[1], "mgsr_cycle1_final_err")):
+            o_it = (o.restart_out - 1) * m + o.n_out
+            if r_it[3] == 1 or ck not in c:
+                assert abs(o_it - r_it[1]) <= 1, key     # tol 1e-15: +-1
+            else:
+                # more than one cycle at tol 1e-15: the first cycle is reproducible (asserted to 1e-10 below), the
+                # later ones start from a residual at the rounding level of x (see the note in the fixture): their
+                # length varies by tens of iterations with the last bit of x -- same number of cycles, count within 20 %
+                assert abs(o_it - r_it[1]) <= 0.2 * r_it[1], key
+                ref1 = np.array(c[ck])
+                assert rel_hist(np.array(o.history[:m]), ref1) < 1e-10, (key, ck)
             assert abs(o.restart_out - r_it[3]) <= 1, key
             assert np.max(np.abs(o.x - 1.0)) < 10 * max(r_l[1], 1e-14), key
 
