@@ -166,6 +166,15 @@ def main():
         print(f"cg {ns}: cg_omp {C[f'cg_omp_{ns}']['iterations']} pcg_omp {C[f'pcg_omp_{ns}']['iterations']} "
               f"pbicgstab_omp {C[f'pbicgstab_omp_{ns}']['iterations']}  {time.time() - t_all:.0f}s", flush=True)
 
+    # ---- the reference drivers' own grid (tests/test_cg.f90:21, tests/test_bicgstab.f90: nsize = 300), OpenMP variants only
+    # (70-90 s each in the interpreter; no per-iteration history: that would be one run per iteration)
+    if not args.quick:
+        C["pcg_omp_300"] = cg_case("conjugate_gradient", "pcg_omp", 300, 1e-9, True, "ax_op", "iter", False)
+        C["cg_omp_300"] = cg_case("conjugate_gradient", "cg_omp", 300, 1e-9, False, "ax_op", "iter", False)
+        C["pbicgstab_omp_300"] = cg_case("bicgstab_mod", "pbicgstab_omp", 300, 1e-9, True, "ax_op", "max_iter", False)
+        print(f"300^2: pcg_omp {C['pcg_omp_300']['iterations']} cg_omp {C['cg_omp_300']['iterations']} "
+              f"pbicgstab_omp {C['pbicgstab_omp_300']['iterations']}  {time.time() - t_all:.0f}s", flush=True)
+
     # ---- dense variants (dense 5-point matrix and Hilbert) ---------------------------------------------------------
     for ns, m in ((6, 10), (8, 20)):
         A = call("poisson", "generate_matrix", nsize=ns)["a"]

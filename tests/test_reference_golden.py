@@ -121,7 +121,8 @@ def test_bicgstab_variants_match_the_reference(ko, ref, name):
             fn(ko.stvec_fn(), b, c["tol"], 100000)
         # rounding differences grow by ~2.5x per BiCGSTAB iteration: counts within a few, same answer
         assert abs(o.iter - c["iterations"]) <= max(2, c["iterations"] // 10), key
-        assert x_diff(o.x, c) < 1e-8, key
+        # two different BiCGSTAB iterates that both satisfy ||r|| < tol: each is within its own error of x = 1
+        assert x_diff(o.x, c) < max(1e-8, 10.0 * c.get("x_err_inf", 0.0)), key
         if "history" in c:
             k = min(8, len(c["history"]), o.history.size)
             assert rel_hist(o.history[:k], c["history"][:k]) < 1e-10, key
