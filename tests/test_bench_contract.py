@@ -1,5 +1,5 @@
-"""The JSON line bench.py prints must keep the driver's contract.  Checked on the committed round-1 lines
-(profiles/): no GPU needed."""
+"""The JSON line bench.py prints must keep the driver's contract.  Checked on the committed round-1 and round-2
+lines (profiles/): no GPU needed."""
 import json
 import os
 
@@ -17,7 +17,9 @@ def _line(name):
 
 
 @pytest.mark.parametrize("name,n", [("r01_bench_n1_final.json", 1), ("r01_bench_cg16384_n2_64n.json", 2),
-                                    ("r01_bench_cg16384_n4_64n.json", 4), ("r01_bench_cg16384_n8_64n.json", 8)])
+                                    ("r01_bench_cg16384_n4_64n.json", 4), ("r01_bench_cg16384_n8_64n.json", 8),
+                                    ("r02_bench_n1.json", 1), ("r02_bench_cg16384_n2.json", 2),
+                                    ("r02_bench_cg16384_n4.json", 4), ("r02_bench_cg16384_n8.json", 8)])
 def test_bench_line_contract(name, n):
     d = _line(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -36,6 +38,15 @@ def test_bench_line_contract(name, n):
     c = d["clocks"]
     assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown",
                                                                         "sw_thermal_slowdown"}
+    if name.startswith("r02"):
+        # round 2: every line, at every N, carries the parity of the timed run against the committed oracle history,
+        # and the N = 1 line carries the other workloads
+        par = d["config"]["parity"]
+        assert par["iterations_compared"] >= 20 and par["max_rel"] < 1e-10, par
+        if n == 1:
+            ex = d["config"]["extras"]
+            assert {"gmres4096", "gmres4096sel", "pcg16384", "bicgstab8192", "hh1024", "gmres300"} <= set(ex)
+            assert all(v["its_per_s"] > 0 for v in ex.values())
     if n == 1:
         # DRAM traffic measured by ncu agrees with the algorithmic bytes of the dominant kernel
         assert r["traffic"] and abs(r["traffic"] / r["algorithmic_bytes_per_launch"] - 1) < 0.05
@@ -48,3 +59,6 @@ def test_strong_scaling_meets_the_north_star():
     one = _line("r01_bench_n1_final.json")["value"]
     eight = _line("r01_bench_cg16384_n8_64n.json")["value"]
     assert eight / one >= 6.0          # BASELINE.json: ">= 6x strong-scaling speedup at 8 GPUs for the CG case"
+    # round 2, all four N on ONE box
+    v = {n: _line(f"r02_bench_cg16384_n{n}.json")["value"] for n in (1, 2, 4, 8)}
+    assert v[8] / v[1] >= 6.8 and v[4] / v[1] >= 3.6 and v[2] / v[1] >= 1.9
