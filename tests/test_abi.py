@@ -79,3 +79,22 @@ def test_cheb_interval_policy_is_host_arithmetic():
         assert out[0] == 1.025 * 8.0 and out[1] == out[0] / ratio
     assert L.kl_cheb_interval_from_ritz(-1.0, 2, out) < 0 and L.kl_cheb_interval_from_ritz(8.0, 0, out) < 0
     assert L.kl_cheb_params_from_ritz(0.01, 8.0, out) == 0 and out[0] == 8.2 and abs(out[1] - 0.2) < 1e-15
+
+
+def test_library_is_sm100a_only_and_links_no_math_library(lib):
+    """The device code is sm_100a and nothing else; the host side links no cuBLAS / cuSPARSE / cuSOLVER / NCCL
+    (NCCL is dlopen'ed by kl_comm_init only), i.e. every kernel on the path is this repo's own."""
+    import shutil
+    import subprocess
+    import gmres_b200 as kl
+    path = kl.library_path()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    elfs = subprocess.run([cuobjdump, "-lelf", path], capture_output=True, text=True).stdout.split("\n")
+    elfs = [e for e in elfs if "ELF file" in e]
+    assert elfs and all("sm_100a" in e for e in elfs), elfs
+    needed = subprocess.run(["readelf", "-d", path], capture_output=True, text=True).stdout
+    libs = re.findall(r"Shared library: \[([^\]]+)\]", needed)
+    assert not [n for n in libs if re.search(r"cublas|cusparse|cusolver|nccl|cudnn|cufft|torch", n)], libs
+    assert os.path.getsize(path) < 15 * 1024 * 1024      # round-1 build was 43.5 MB (522 kernels)
