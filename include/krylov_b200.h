@@ -132,8 +132,9 @@ enum {
     KL_OPT_STENCIL_ROWS = 13, /* grid lines per CTA of the temporally blocked kernels (0 = heuristic)       */
     KL_OPT_INLINE_ALLREDUCE = 14, /* multi-GPU with peer memory: 1 (default) = the last block of a reducing kernel does
                                  the NVLink all-reduce and the scalar recurrence itself; 0 = separate kernels  */
-    KL_OPT_PDL = 15,          /* 1 (default): the fused CG kernels are launched with programmatic dependent launch, so
-                                 the prologue of one overlaps the tail of the other; 0: plain stream order      */
+    KL_OPT_PDL = 15,          /* 1 (default): the fused CG kernels and, on one GPU, every kernel of a GMRES / Householder
+                                 restart cycle are launched with programmatic dependent launch, so the launch and
+                                 prologue of one overlap the tail of the other; 0: plain stream order            */
     KL_OPT_STENCIL_TAIL = 17, /* lines per CTA in the tapered tail of the stencil kernels' grids: -1 (default) = a quarter
                                  of the regular tile height, 0 = off                                            */
     KL_OPT_STENCIL_STAGGER = 18, /* 1: CTA heights of the stencil kernels staggered (5/8 .. 11/8 of the mean) so that CTAs
