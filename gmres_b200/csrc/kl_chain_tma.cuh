@@ -115,8 +115,9 @@ struct ChainBase {
 #endif
     // LEAN: interior CTAs run their middle hexads through a copy of the march without out-of-domain masks (see
     // k_chain_tma).  Pays from L = 3 on (L - 1 masked levels; 322 -> 292 us at L = 3, 703 -> 643 us at L = 6); at
-    // L <= 2 and for the multi-input chains the checked first hexad it needs costs more than the masks (+9 %).
-    static constexpr bool LEAN = NIN_ == 1 && L_ >= 3;
+    // L <= 2 the checked first hexad it needs costs more than the masks (+9 %; BiCGSTAB's two-level chains included).
+    // The three-input continuation chunks (L >= 3) gain like the single-input ones: degree 8 = 4 + 4: ~1040 -> 940 us.
+    static constexpr bool LEAN = L_ >= 3;     // (also the three-input continuation chunks of degrees 7..12)
     // Two columns per thread.  A four-column variant (half the shuffles and per-line overhead per point, but
     // ~160 registers at L = 2, i.e. 3 CTAs per SM instead of 6) measured 10-50 % slower: these kernels are
     // dependent FP64 chains behind a shuffle and live on thread-level parallelism.
