@@ -122,7 +122,7 @@ def main():
 
     gm = [(16, 10, 1e-8), (16, 10, 1e-15), (24, 20, 1e-8), (32, 30, 1e-10)]
     if not args.quick:
-        gm += [(48, 30, 1e-8), (64, 95, 1e-8)]
+        gm += [(48, 30, 1e-8), (64, 95, 1e-8), (100, 95, 1e-8)]      # 100^2: the preconditioned variants only (below)
     for ns, m, tol in gm:
         tag = f"{ns}_{m}_{tol:g}"
         C[f"gmres_mgsr_omp_{tag}"] = gmres_case("gmres_mgsr_mod", "gmres_mgsr_omp", ns, m, tol, "max_restarts", True)
@@ -130,7 +130,7 @@ def main():
                                                cycles_hist=ns <= 24)
         C[f"gmres_hh_prec_omp_{tag}"] = gmres_case("gmres_hh_mod", "gmres_hh_prec_omp", ns, m, tol, "stages", True,
                                                    cycles_hist=ns <= 32)
-        if ns <= 32:
+        if ns <= 32:      # unpreconditioned Householder GMRES needs hundreds of cycles on the larger grids
             C[f"gmres_hh_omp_{tag}"] = gmres_case("gmres_hh_mod", "gmres_hh_omp", ns, m, tol, "stages", False,
                                                   cycles_hist=ns <= 24)
         print(f"gmres {tag}: {C[f'gmres_mgsr_omp_{tag}']['iterations']} its "
